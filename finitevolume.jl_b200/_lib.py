@@ -1,0 +1,79 @@
+"""ctypes binding of libfvb200.so (include/fvb200.h).  No fallbacks: if the shared library
+has not been built, or no CUDA device is present, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfvb200.so")
+UNIQUE_ID_BYTES = 128
+NSLOT = 8
+
+# every symbol include/fvb200.h declares (tests check the built library exports them all)
+SYMBOLS = [
+    "fvb_version", "fvb_last_error", "fvb_device_count", "fvb_create", "fvb_destroy",
+    "fvb_comm_unique_id", "fvb_comm_init", "fvb_assemble", "fvb_update_values", "fvb_sizes",
+    "fvb_get_csr", "fvb_get_b", "fvb_get_diag", "fvb_get_freenode", "fvb_get_nodei2freenodei",
+    "fvb_get_halo_cols", "fvb_set_halo_plan", "fvb_solve", "fvb_spmv", "fvb_vec_upload",
+    "fvb_vec_download", "fvb_vec_copy", "fvb_vec_load_b", "fvb_vec_diffnorm", "fvb_set_storage",
+    "fvb_step", "fvb_vec_to_nodes", "fvb_time_spmv", "fvb_get_timings", "fvb_sync",
+]
+
+
+class Timings(C.Structure):
+    _fields_ = [("h2d_ms", C.c_double), ("assemble_ms", C.c_double), ("solve_ms", C.c_double),
+                ("d2h_ms", C.c_double), ("spmv_ms_total", C.c_double), ("kernel_launches", C.c_int64)]
+
+
+class FVBError(RuntimeError):
+    """Non-zero fvb_status.  `.status` holds the code (1 = bad input: the cases where the
+    reference calls error())."""
+
+    def __init__(self, status, msg):
+        super().__init__(msg)
+        self.status = status
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  finitevolume.jl_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L.fvb_last_error.restype = C.c_char_p
+        for name in SYMBOLS:
+            if name != "fvb_last_error":
+                getattr(L, name).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise FVBError(status, lib().fvb_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    """void* of a numpy array (must be C-contiguous), an int device address, or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    assert a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)

@@ -1,0 +1,347 @@
+"""Host-side mirror of the reference's call surface for the assemble -> solve path.
+
+Function names, argument order and meaning, return tuples and error behaviour follow
+madsjulia/FiniteVolume.jl (file:line cites are relative to the reference checkout), so the
+parity tests read like the reference's own tests.  Every function here drives
+libfvb200.so through ctypes; there is no CPU implementation behind any of them.
+
+Index conventions are Julia's: node ids, Dirichlet nodes, metaindex values and the
+returned colptr/rowval are 1-based int64.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, f64, i64, lib, ptr
+
+SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)  # IterativeSolvers' default relative tolerance
+DEFAULT_MAXITER = 100_000
+
+
+def _pairs(neighbors) -> np.ndarray:
+    """[(n1,n2),...] / (F,2) / flat 2F -> flat int64[2F] (the memory image of
+    Array{Pair{Int,Int},1})."""
+    return i64(np.asarray(neighbors, dtype=np.int64)).reshape(-1)
+
+
+def _metaindex_table(metaindex, F):
+    """The reference accepts any callable i -> index (src/FiniteVolume.jl:75); the C ABI
+    takes its table.  None means the identity."""
+    if metaindex is None:
+        return None
+    if callable(metaindex):
+        return np.fromiter((metaindex(i) for i in range(1, F + 1)), dtype=np.int64, count=F)
+    return i64(metaindex)
+
+
+@dataclass
+class ConvergenceHistory:
+    """What callers of the reference read from IterativeSolvers.ConvergenceHistory
+    (examples/box_model/ex_piml_data.jl:46, examples/waffle/ex.jl:25)."""
+    isconverged: bool
+    iters: int
+    data: dict = field(default_factory=dict)
+
+
+class System:
+    """One assembled problem resident on one GPU (an fvb_handle)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().fvb_create(C.c_int(device), C.byref(self._h)))
+        self.device = device
+        self.node_lo = 1
+        self.node_hi = 0
+        self.nranks = 1
+        self.rank = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().fvb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- multi-GPU ---------------------------------------------------------------------
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * _lib.UNIQUE_ID_BYTES)()
+        check(lib().fvb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        buf = (C.c_uint8 * _lib.UNIQUE_ID_BYTES).from_buffer_copy(uid)
+        check(lib().fvb_comm_init(self._h, C.c_int(nranks), C.c_int(rank), buf))
+        self.nranks, self.rank = nranks, rank
+
+    # ---- assembly ----------------------------------------------------------------------
+    def assemble(self, neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
+                 metaindex=None, logtransformconductivity=False, n_nodes=None, node_range=None):
+        """assembleA + assembleb (src/FiniteVolume.jl:75-139).  With node_range=(lo,hi)
+        (1-based inclusive) `sources` is the owned slice and `neighbors` etc. are the faces
+        touching owned nodes, in global face order."""
+        nb = _pairs(neighbors)
+        F = nb.size // 2
+        aol = f64(areasoverlengths)
+        cond = f64(conductivities)
+        src = f64(sources)
+        dn = i64(dirichletnodes)
+        dh = f64(dirichletheads)
+        if aol.size != F:
+            raise ValueError("areasoverlengths and neighbors differ in length")
+        if dn.size != dh.size:
+            raise ValueError("dirichletnodes and dirichletheads differ in length")
+        meta = _metaindex_table(metaindex, F)
+        if meta is None and cond.size < F:
+            raise IndexError("conductivities is shorter than neighbors")  # Julia: BoundsError
+        N = int(src.size if n_nodes is None else n_nodes)
+        lo, hi = (1, N) if node_range is None else (int(node_range[0]), int(node_range[1]))
+        if src.size != hi - lo + 1:
+            raise ValueError("sources must cover exactly the owned node range")
+        check(lib().fvb_assemble(self._h, C.c_int64(N), C.c_int64(lo), C.c_int64(hi), C.c_int64(F), ptr(nb), ptr(aol),
+                                 ptr(cond), C.c_int64(cond.size), ptr(meta), C.c_int(int(bool(logtransformconductivity))),
+                                 ptr(src), C.c_int64(dn.size), ptr(dn), ptr(dh)))
+        self.node_lo, self.node_hi = lo, hi
+        self._logk = bool(logtransformconductivity)
+        return self
+
+    def update_values(self, conductivities, sources=None, dirichletheads=None, logtransformconductivity=None):
+        cond = f64(conductivities)
+        logk = self._logk if logtransformconductivity is None else bool(logtransformconductivity)
+        src = None if sources is None else f64(sources)
+        dh = None if dirichletheads is None else f64(dirichletheads)
+        check(lib().fvb_update_values(self._h, ptr(cond), C.c_int64(cond.size), C.c_int(int(logk)), ptr(src), ptr(dh)))
+        return self
+
+    def sizes(self):
+        v = [C.c_int64() for _ in range(5)]
+        check(lib().fvb_sizes(self._h, *[C.byref(x) for x in v]))
+        return dict(nf_local=v[0].value, nnz_local=v[1].value, row_start=v[2].value, nf_global=v[3].value,
+                    n_halo=v[4].value)
+
+    @property
+    def n_own_nodes(self):
+        return self.node_hi - self.node_lo + 1
+
+    def csr(self):
+        s = self.sizes()
+        p = np.empty(s["nf_local"] + 1, np.int64)
+        idx = np.empty(s["nnz_local"], np.int64)
+        val = np.empty(s["nnz_local"], np.float64)
+        check(lib().fvb_get_csr(self._h, ptr(p), ptr(idx), ptr(val)))
+        return p, idx, val
+
+    def b(self):
+        out = np.empty(self.sizes()["nf_local"], np.float64)
+        check(lib().fvb_get_b(self._h, ptr(out)))
+        return out
+
+    def diag(self):
+        out = np.empty(self.sizes()["nf_local"], np.float64)
+        check(lib().fvb_get_diag(self._h, ptr(out)))
+        return out
+
+    def freenode(self):
+        out = np.empty(self.n_own_nodes, np.uint8)
+        check(lib().fvb_get_freenode(self._h, ptr(out)))
+        return out.astype(bool)
+
+    def nodei2freenodei(self):
+        out = np.empty(self.n_own_nodes, np.int64)
+        check(lib().fvb_get_nodei2freenodei(self._h, ptr(out)))
+        return out
+
+    def halo_cols(self):
+        out = np.empty(self.sizes()["n_halo"], np.int64)
+        check(lib().fvb_get_halo_cols(self._h, ptr(out)))
+        return out
+
+    def set_halo_plan(self, peer_ranks, send_counts, send_rows, recv_counts):
+        pr = np.ascontiguousarray(peer_ranks, np.int32)
+        sc = i64(send_counts)
+        sr = np.ascontiguousarray(send_rows, np.int32)
+        rc = i64(recv_counts)
+        check(lib().fvb_set_halo_plan(self._h, C.c_int(pr.size), ptr(pr), ptr(sc), ptr(sr), ptr(rc)))
+
+    # ---- solve ---------------------------------------------------------------------------
+    def solve(self, rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER, x0=None, want_head=True, want_x=False, hist_cap=None,
+              head_out=None):
+        s = self.sizes()
+        x0a = None if x0 is None else f64(x0)
+        head = None
+        if want_head:
+            head = head_out if head_out is not None else np.empty(self.n_own_nodes, np.float64)
+        x = np.empty(s["nf_local"], np.float64) if want_x else None
+        cap = int(min(maxiter, 1 << 24) if hist_cap is None else hist_cap)
+        hist = np.empty(max(cap, 1), np.float64)
+        iters = C.c_int64()
+        conv = C.c_int()
+        check(lib().fvb_solve(self._h, C.c_double(rtol), C.c_int64(int(maxiter)), ptr(x0a), ptr(head), ptr(x),
+                              C.byref(iters), C.byref(conv), ptr(hist), C.c_int64(cap)))
+        ch = ConvergenceHistory(bool(conv.value), int(iters.value), {"resnorm": hist[:min(iters.value, cap)].copy()})
+        return head, x, ch
+
+    def spmv(self, x, alpha=1.0, beta=0.0, y=None):
+        xa = f64(x)
+        ya = np.zeros_like(xa) if y is None else f64(y).copy()
+        check(lib().fvb_spmv(self._h, C.c_double(alpha), ptr(xa), C.c_double(beta), ptr(ya)))
+        return ya
+
+    # ---- transient, device-resident vectors --------------------------------------------------
+    def vec_upload(self, slot, v):
+        check(lib().fvb_vec_upload(self._h, C.c_int(slot), ptr(f64(v))))
+
+    def vec_download(self, slot):
+        out = np.empty(self.sizes()["nf_local"], np.float64)
+        check(lib().fvb_vec_download(self._h, C.c_int(slot), ptr(out)))
+        return out
+
+    def vec_copy(self, dst, src):
+        check(lib().fvb_vec_copy(self._h, C.c_int(dst), C.c_int(src)))
+
+    def vec_load_b(self, slot):
+        check(lib().fvb_vec_load_b(self._h, C.c_int(slot)))
+
+    def vec_diffnorm(self, a, b):
+        out = C.c_double()
+        check(lib().fvb_vec_diffnorm(self._h, C.c_int(a), C.c_int(b), C.byref(out)))
+        return out.value
+
+    def set_storage(self, Ss, volumes_owned):
+        v = None if volumes_owned is None else f64(volumes_owned)
+        check(lib().fvb_set_storage(self._h, C.c_double(Ss), ptr(v)))
+
+    def step(self, rhs_slot, u_slot, dt, out_slot, adjoint=False, rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER):
+        iters = C.c_int64()
+        conv = C.c_int()
+        check(lib().fvb_step(self._h, C.c_int(rhs_slot), C.c_int(u_slot), C.c_double(dt), C.c_int(out_slot),
+                             C.c_int(int(adjoint)), C.c_double(rtol), C.c_int64(int(maxiter)), C.byref(iters),
+                             C.byref(conv)))
+        return int(iters.value), bool(conv.value)
+
+    def vec_to_nodes(self, slot):
+        out = np.empty(self.n_own_nodes, np.float64)
+        check(lib().fvb_vec_to_nodes(self._h, C.c_int(slot), ptr(out)))
+        return out
+
+    # ---- measurement ------------------------------------------------------------------------
+    def time_spmv(self, warmup=3, reps=20):
+        out = C.c_double()
+        check(lib().fvb_time_spmv(self._h, C.c_int(warmup), C.c_int(reps), C.byref(out)))
+        return out.value
+
+    def timings(self):
+        t = _lib.Timings()
+        check(lib().fvb_get_timings(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in t._fields_}
+
+    def sync(self):
+        check(lib().fvb_sync(self._h))
+
+
+class SparseMatrixCSC:
+    """The `A` of the reference's return tuples: a SparseMatrixCSC{Float64,Int64} image whose
+    arrays are fetched from the GPU on first access (A is symmetric, so the CSR arrays kept
+    on the device are its CSC arrays; src/FiniteVolume.jl:107)."""
+
+    def __init__(self, system: System):
+        self._sys = system
+        s = system.sizes()
+        self.m = self.n = s["nf_global"]
+        self._arrays = None
+
+    def _fetch(self):
+        if self._arrays is None:
+            self._arrays = self._sys.csr()
+        return self._arrays
+
+    @property
+    def colptr(self):
+        return self._fetch()[0]
+
+    @property
+    def rowval(self):
+        return self._fetch()[1]
+
+    @property
+    def nzval(self):
+        return self._fetch()[2]
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def toscipy(self):
+        import scipy.sparse as sp
+        p, i, v = self._fetch()
+        return sp.csc_matrix((v, i - 1, p - 1), shape=(self.m, self.n))
+
+    def __matmul__(self, x):
+        """A * x on the GPU (examples/waffle/ex.jl:16 computes A*head[freenode]-b)."""
+        return self._sys.spmv(x)
+
+
+# ======================================================================================
+# Reference-named functions
+# ======================================================================================
+def getfreenodes(n, dirichletnodes, device=0):
+    """src/FiniteVolume.jl:32-44 -> (freenode::Vector{Bool}, nodei2freenodei::Vector{Int})."""
+    s = System(device)
+    try:
+        s.assemble(np.empty((0, 2), np.int64), [], [], np.zeros(n), dirichletnodes, np.zeros(len(dirichletnodes)))
+        return s.freenode(), s.nodei2freenodei()
+    finally:
+        s.close()
+
+
+def assembleA(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
+              metaindex=None, logtransformconductivity=False, device=0) -> SparseMatrixCSC:
+    """src/FiniteVolume.jl:75-108."""
+    s = System(device).assemble(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
+                                metaindex, logtransformconductivity)
+    return SparseMatrixCSC(s)
+
+
+def assembleb(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
+              metaindex=None, logtransformconductivity=False, device=0) -> np.ndarray:
+    """src/FiniteVolume.jl:110-139."""
+    s = System(device)
+    try:
+        s.assemble(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
+                   metaindex, logtransformconductivity)
+        return s.b()
+    finally:
+        s.close()
+
+
+def freenodes2nodes(result, sources, dirichletnodes, dirichletheads, device=0):
+    """src/FiniteVolume.jl:141-155 -> (head, freenode, nodei2freenodei)."""
+    s = System(device)
+    try:
+        s.assemble(np.empty((0, 2), np.int64), [], [], sources, dirichletnodes, dirichletheads)
+        s.vec_upload(0, result)
+        return s.vec_to_nodes(0), s.freenode(), s.nodei2freenodei()
+    finally:
+        s.close()
+
+
+def solvediffusion(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
+                   maxiter=DEFAULT_MAXITER, rtol=SQRT_EPS, metaindex=None, logtransformconductivity=False, device=0):
+    """src/FiniteVolume.jl:157-165 -> (head, ch, A, b, freenode).
+
+    Differences from the reference, both mandated by north_star: the preconditioner is
+    Jacobi instead of Ruge-Stueben AMG, so `maxiter` counts Jacobi-PCG iterations (default
+    raised from 400 accordingly); `rtol` exposes IterativeSolvers' `tol` (same default)."""
+    s = System(device).assemble(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
+                                metaindex, logtransformconductivity)
+    head, _, ch = s.solve(rtol=rtol, maxiter=maxiter)
+    return head, ch, SparseMatrixCSC(s), s.b(), s.freenode()

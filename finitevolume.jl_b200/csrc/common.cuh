@@ -1,0 +1,105 @@
+// common.cuh -- shared declarations of libfvb200 (handle layout, error plumbing).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fvb200.h"
+
+namespace fvb {
+
+extern thread_local std::string g_last_error;
+int set_error(int code, const std::string &msg);
+
+#define FVB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return fvb::set_error(e__ == cudaErrorMemoryAllocation ? FVB_ERR_OOM : FVB_ERR_CUDA, \
+                            std::string(#expr) + ": " + cudaGetErrorString(e__));        \
+  } while (0)
+
+#define FVB_TRY(expr)              \
+  do {                             \
+    int s__ = (expr);              \
+    if (s__ != FVB_OK) return s__; \
+  } while (0)
+
+constexpr int kBlock = 256;
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Device-resident scalars of the PCG recurrence (IterativeSolvers.cg 0.8.1 names:
+// rho = c.r, uc = u.Au, resid = ||r||).  Lives in device memory; a copy is polled by the
+// host every few iterations through pinned memory.
+struct PcgScal {
+  double rho, rho_prev, uc, resid, resid0, reltol, tol;
+  double red[4];       // local partial sums awaiting the (optional) all-reduce
+  long long iter, maxiter, hist_cap;
+  int done, converged;
+};
+
+struct Comm;  // nccl_dyn.h
+
+}  // namespace fvb
+
+struct fvb_handle_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  int num_sms = 148;
+
+  // ---- partition -------------------------------------------------------------------
+  int64_t n_nodes = 0;          // global N
+  int64_t node_lo = 0, node_hi = 0;  // 0-based [lo, hi)
+  int64_t n_own_nodes = 0;
+  int64_t nf_local = 0, nf_global = 0, row_start = 0;  // row_start: 0-based global free idx
+  int64_t n_halo = 0, nnz = 0;
+  int64_t n_faces = 0, n_dirichlet = 0, n_adj = 0;
+  bool assembled = false;
+
+  // ---- retained device arrays ---------------------------------------------------------
+  int32_t *nodemap = nullptr;   // [n_own_nodes] >=0 local free row, <0: -1-dirichlet slot
+  int32_t *row2node = nullptr;  // [nf_local] local node index of each row
+  double *sources = nullptr;    // [n_own_nodes]
+  double *dheads = nullptr;     // [n_dirichlet]
+  double *aol = nullptr;        // [n_faces]
+  int64_t *meta = nullptr;      // [n_faces] or null
+  double *cface = nullptr;      // [n_faces] per-face conductance
+  int32_t *adjptr = nullptr;    // [nf_local+1]
+  int32_t *adj_face = nullptr;  // [n_adj] sorted per row by (column key, face)
+  int32_t *adj_col = nullptr;   // [n_adj] local col / nf_local+halo / -1-dirichlet slot
+  int64_t *halo_glob = nullptr; // [n_halo] 0-based global free idx, ascending
+  int32_t *rowptr = nullptr;    // [nf_local+1]
+  int32_t *colidx = nullptr;    // [nnz]
+  double *vals = nullptr;       // [nnz]
+  double *b = nullptr, *diag = nullptr;  // [nf_local]
+  std::vector<int64_t> halo_host;
+
+  // ---- solver workspace ---------------------------------------------------------------
+  double *x = nullptr, *r = nullptr, *u = nullptr, *c = nullptr, *dinv = nullptr;  // u: nf_local+n_halo
+  double *rhs = nullptr;        // transient right-hand side
+  double *Dvec = nullptr;       // Ss*vol per free row, or null (identity)
+  double *slots[FVB_NSLOT] = {};
+  double *partials = nullptr;   // [2 * max grid] block partial sums
+  unsigned int *ticket = nullptr;
+  fvb::PcgScal *scal = nullptr;       // device
+  fvb::PcgScal *scal_host = nullptr;  // pinned, 2 entries
+  double *hist = nullptr;
+  int64_t hist_cap = 0;
+  double *xio = nullptr, *yio = nullptr;  // staging for fvb_spmv host vectors
+
+  // ---- multi-GPU ------------------------------------------------------------------------
+  int nranks = 1, rank = 0;
+  fvb::Comm *comm = nullptr;
+  std::vector<int> peers;
+  std::vector<int64_t> send_counts, recv_counts;
+  int32_t *send_rows = nullptr;
+  double *sendbuf = nullptr;
+  int64_t n_send = 0;
+  bool halo_ready = false;
+
+  fvb_timings tm = {};
+};

@@ -1,0 +1,863 @@
+// fvb200.cu -- the C ABI of libfvb200.so (include/fvb200.h) over the sm_100a kernels in
+// assemble.cuh / spmv.cuh / pcg.cuh.  Host code here only allocates, orders launches and
+// moves data; there is no CPU implementation of any part of the path.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "assemble.cuh"
+#include "common.cuh"
+#include "nccl_dyn.h"
+#include "pcg.cuh"
+#include "scan.cuh"
+#include "spmv.cuh"
+
+namespace fvb {
+thread_local std::string g_last_error;
+int set_error(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+}  // namespace fvb
+
+using namespace fvb;
+
+#define FVB_NCCL(expr)                                                                          \
+  do {                                                                                          \
+    ncclResult_t r__ = (expr);                                                                  \
+    if (r__ != ncclSuccess)                                                                     \
+      return set_error(FVB_ERR_NCCL, std::string(#expr) + ": " + nccl().GetErrorString(r__));   \
+  } while (0)
+
+namespace {
+
+template <typename T>
+int dalloc(T **p, int64_t n) {
+  *p = nullptr;
+  size_t bytes = sizeof(T) * (size_t)std::max<int64_t>(n, 1);
+  cudaError_t e = cudaMalloc((void **)p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(FVB_ERR_OOM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+  }
+  return FVB_OK;
+}
+template <typename T>
+void dfree(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+int grid_for(int64_t n) { return std::max(1, cdiv(n, kBlock)); }
+int vgrid(fvb_handle h, int64_t n) { return std::max(1, std::min(cdiv(n, kBlock), h->num_sms * 8)); }
+
+void free_problem(fvb_handle h) {
+  dfree(h->nodemap); dfree(h->row2node); dfree(h->sources); dfree(h->dheads); dfree(h->aol);
+  dfree(h->meta); dfree(h->cface); dfree(h->adjptr); dfree(h->adj_face); dfree(h->adj_col);
+  dfree(h->halo_glob); dfree(h->rowptr); dfree(h->colidx); dfree(h->vals); dfree(h->b); dfree(h->diag);
+  dfree(h->x); dfree(h->r); dfree(h->u); dfree(h->c); dfree(h->dinv); dfree(h->rhs); dfree(h->Dvec);
+  for (auto &s : h->slots) dfree(s);
+  dfree(h->partials); dfree(h->hist); dfree(h->xio); dfree(h->yio);
+  dfree(h->send_rows); dfree(h->sendbuf);
+  h->hist_cap = 0;
+  h->assembled = false;
+  h->halo_ready = false;
+  h->peers.clear(); h->send_counts.clear(); h->recv_counts.clear();
+  h->halo_host.clear();
+  h->n_send = 0;
+}
+
+int check_handle(fvb_handle h, bool need_assembled) {
+  if (!h) return set_error(FVB_ERR_BAD_INPUT, "null handle");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  if (need_assembled && !h->assembled) return set_error(FVB_ERR_STATE, "fvb_assemble has not succeeded on this handle");
+  return FVB_OK;
+}
+
+int ensure_workspace(fvb_handle h) {
+  const int64_t n = h->nf_local;
+  if (!h->x) {
+    FVB_TRY(dalloc(&h->x, n)); FVB_TRY(dalloc(&h->r, n)); FVB_TRY(dalloc(&h->c, n));
+    FVB_TRY(dalloc(&h->u, n + h->n_halo)); FVB_TRY(dalloc(&h->dinv, n)); FVB_TRY(dalloc(&h->rhs, n));
+    FVB_TRY(dalloc(&h->partials, 2 * (int64_t)std::max(cdiv(n, kSpmvRows), h->num_sms * 8) + 2));
+    FVB_CUDA(cudaMemsetAsync(h->u, 0, sizeof(double) * (size_t)std::max<int64_t>(n + h->n_halo, 1), h->stream));
+  }
+  return FVB_OK;
+}
+
+int ensure_hist(fvb_handle h, int64_t cap) {
+  cap = std::max<int64_t>(std::min<int64_t>(cap, 1 << 24), 1);
+  if (cap > h->hist_cap) {
+    dfree(h->hist);
+    FVB_TRY(dalloc(&h->hist, cap));
+    h->hist_cap = cap;
+  }
+  return FVB_OK;
+}
+
+// ---- multi-rank plumbing -----------------------------------------------------------------
+int halo_exchange(fvb_handle h, double *vec) {
+  if (h->nranks == 1) return FVB_OK;
+  if (!h->halo_ready) return set_error(FVB_ERR_STATE, "fvb_set_halo_plan has not been called on this rank");
+  if (h->n_send > 0) {
+    k_pack<<<grid_for(h->n_send), kBlock, 0, h->stream>>>(h->n_send, h->send_rows, vec, h->sendbuf);
+    h->tm.kernel_launches++;
+  }
+  NcclApi &N = nccl();
+  FVB_NCCL(N.GroupStart());
+  int64_t so = 0, ro = 0;
+  for (size_t p = 0; p < h->peers.size(); ++p) {
+    if (h->send_counts[p] > 0)
+      FVB_NCCL(N.Send(h->sendbuf + so, (size_t)h->send_counts[p], ncclDouble, h->peers[p], h->comm->comm, h->stream));
+    if (h->recv_counts[p] > 0)
+      FVB_NCCL(N.Recv(vec + h->nf_local + ro, (size_t)h->recv_counts[p], ncclDouble, h->peers[p], h->comm->comm, h->stream));
+    so += h->send_counts[p];
+    ro += h->recv_counts[p];
+  }
+  FVB_NCCL(N.GroupEnd());
+  return FVB_OK;
+}
+
+int allreduce_sum(fvb_handle h, double *dev, int count) {
+  if (h->nranks == 1) return FVB_OK;
+  FVB_NCCL(nccl().AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, h->comm->comm, h->stream));
+  return FVB_OK;
+}
+
+// c = (A + sigma*D) vec, vec has halo room.  With dot: also u.Au into scal (CG use).
+int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot) {
+  FVB_TRY(halo_exchange(h, vec));
+  const int n = (int)h->nf_local;
+  if (n == 0) return FVB_OK;
+  const int grid = cdiv(n, kSpmvRows);
+  const int fin = h->nranks == 1 ? 1 : 0;
+  if (dot)
+    k_spmv<true><<<grid, kSpmvRows, 0, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
+                                                     h->partials, h->ticket, h->scal, fin);
+  else
+    k_spmv<false><<<grid, kSpmvRows, 0, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
+                                                      h->partials, h->ticket, h->scal, fin);
+  h->tm.kernel_launches++;
+  return FVB_OK;
+}
+
+// Jacobi-PCG on (A + sigma*D) x = rhs.  x0 (if any) already sits in h->x.  Result in h->x.
+int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double rtol, int64_t maxiter,
+            int64_t *iters, int *converged) {
+  const int64_t n = h->nf_local;
+  cudaStream_t st = h->stream;
+  const int fin = h->nranks == 1 ? 1 : 0;
+  const int vg = vgrid(h, n);
+  FVB_TRY(ensure_hist(h, maxiter));
+  k_set_scal<<<1, 1, 0, st>>>(h->scal, rtol, (long long)maxiter, (long long)h->hist_cap);
+  k_make_dinv<<<vg, kBlock, 0, st>>>(n, h->diag, h->Dvec, sigma, h->dinv);
+  h->tm.kernel_launches += 2;
+  if (have_x0) {
+    FVB_CUDA(cudaMemcpyAsync(h->u, h->x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    FVB_TRY(launch_spmv(h, h->u, h->c, sigma, false));
+  }
+  k_pcg_init<<<vg, kBlock, 0, st>>>(n, rhs, h->c, have_x0 ? 1 : 0, h->dinv, h->x, h->r, h->partials, h->ticket,
+                                    h->scal, fin);
+  h->tm.kernel_launches++;
+  if (!fin) {
+    FVB_TRY(allreduce_sum(h, h->scal->red, 2));
+    k_fin_init<<<1, 1, 0, st>>>(h->scal);
+    h->tm.kernel_launches++;
+  }
+  // Enqueue iterations in batches; poll the device scalars one batch behind so the GPU
+  // never waits for the host.
+  int64_t enq = 0;
+  int batch = 8, slot = 0;
+  bool have_prev = false;
+  bool stop = false;
+  while (!stop) {
+    int64_t todo = std::min<int64_t>(batch, maxiter - enq);
+    for (int64_t it = 0; it < todo; ++it) {
+      k_update_u<<<vg, kBlock, 0, st>>>(n, h->dinv, h->r, h->u, h->scal);
+      h->tm.kernel_launches++;
+      FVB_TRY(launch_spmv(h, h->u, h->c, sigma, true));
+      if (!fin) {
+        FVB_TRY(allreduce_sum(h, h->scal->red, 1));
+        k_fin_uc<<<1, 1, 0, st>>>(h->scal);
+        h->tm.kernel_launches++;
+      }
+      k_update_xr<<<vg, kBlock, 0, st>>>(n, h->u, h->c, h->dinv, h->x, h->r, h->partials, h->ticket, h->scal,
+                                         h->hist, fin);
+      h->tm.kernel_launches++;
+      if (!fin) {
+        FVB_TRY(allreduce_sum(h, h->scal->red, 2));
+        k_fin_iter<<<1, 1, 0, st>>>(h->scal, h->hist);
+        h->tm.kernel_launches++;
+      }
+    }
+    enq += todo;
+    FVB_CUDA(cudaMemcpyAsync(&h->scal_host[slot], h->scal, sizeof(PcgScal), cudaMemcpyDeviceToHost, st));
+    FVB_CUDA(cudaEventRecord(h->ev[6 + slot], st));
+    if (have_prev) {
+      FVB_CUDA(cudaEventSynchronize(h->ev[6 + (slot ^ 1)]));
+      if (h->scal_host[slot ^ 1].done) stop = true;
+    }
+    have_prev = true;
+    slot ^= 1;
+    if (enq >= maxiter) stop = true;
+    if (batch < 64) batch *= 2;
+  }
+  FVB_CUDA(cudaStreamSynchronize(st));
+  FVB_CUDA(cudaMemcpy(&h->scal_host[0], h->scal, sizeof(PcgScal), cudaMemcpyDeviceToHost));
+  if (iters) *iters = h->scal_host[0].iter;
+  if (converged) *converged = h->scal_host[0].converged;
+  FVB_CUDA(cudaGetLastError());
+  return FVB_OK;
+}
+
+bool valid_slot(int s) { return s >= 0 && s < FVB_NSLOT; }
+int ensure_slot(fvb_handle h, int s) {
+  if (!valid_slot(s)) return set_error(FVB_ERR_BAD_INPUT, "vector slot out of range");
+  if (!h->slots[s]) {
+    FVB_TRY(dalloc(&h->slots[s], h->nf_local));
+    FVB_CUDA(cudaMemsetAsync(h->slots[s], 0, sizeof(double) * (size_t)std::max<int64_t>(h->nf_local, 1), h->stream));
+  }
+  return FVB_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int fvb_version(void) { return 100; }
+const char *fvb_last_error(void) { return g_last_error.c_str(); }
+
+int fvb_device_count(int *count) {
+  FVB_CUDA(cudaGetDeviceCount(count));
+  return FVB_OK;
+}
+
+int fvb_create(int device, fvb_handle *out) {
+  if (!out) return set_error(FVB_ERR_BAD_INPUT, "null out pointer");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_error(FVB_ERR_CUDA, "no CUDA device available (libfvb200 has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return set_error(FVB_ERR_BAD_INPUT, "device index out of range");
+  FVB_CUDA(cudaSetDevice(device));
+  fvb_handle h = new fvb_handle_s();
+  h->device = device;
+  FVB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto &ev : h->ev) FVB_CUDA(cudaEventCreate(&ev));
+  FVB_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+  FVB_TRY(dalloc(&h->scal, 1));
+  FVB_TRY(dalloc(&h->ticket, 4));
+  FVB_CUDA(cudaMemset(h->ticket, 0, 4 * sizeof(unsigned int)));
+  FVB_CUDA(cudaMemset(h->scal, 0, sizeof(PcgScal)));
+  FVB_CUDA(cudaMallocHost((void **)&h->scal_host, 2 * sizeof(PcgScal)));
+  *out = h;
+  return FVB_OK;
+}
+
+int fvb_destroy(fvb_handle h) {
+  if (!h) return FVB_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_problem(h);
+  if (h->comm) {
+    if (h->comm->comm) nccl().CommDestroy(h->comm->comm);
+    delete h->comm;
+  }
+  dfree(h->scal); dfree(h->ticket);
+  if (h->scal_host) cudaFreeHost(h->scal_host);
+  for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return FVB_OK;
+}
+
+int fvb_comm_unique_id(uint8_t id[FVB_UNIQUE_ID_BYTES]) {
+  static_assert(sizeof(ncclUniqueId) == FVB_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  std::string why = nccl().load();
+  if (!why.empty()) return set_error(FVB_ERR_NCCL, why);
+  ncclUniqueId uid;
+  FVB_NCCL(nccl().GetUniqueId(&uid));
+  memcpy(id, &uid, FVB_UNIQUE_ID_BYTES);
+  return FVB_OK;
+}
+
+int fvb_comm_init(fvb_handle h, int nranks, int rank, const uint8_t id[FVB_UNIQUE_ID_BYTES]) {
+  FVB_TRY(check_handle(h, false));
+  if (nranks < 1 || rank < 0 || rank >= nranks) return set_error(FVB_ERR_BAD_INPUT, "bad rank/nranks");
+  h->nranks = nranks;
+  h->rank = rank;
+  if (nranks == 1) return FVB_OK;
+  std::string why = nccl().load();
+  if (!why.empty()) return set_error(FVB_ERR_NCCL, why);
+  ncclUniqueId uid;
+  memcpy(&uid, id, FVB_UNIQUE_ID_BYTES);
+  h->comm = new Comm();
+  FVB_NCCL(nccl().CommInitRank(&h->comm->comm, nranks, uid, rank));
+  return FVB_OK;
+}
+
+int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_hi1, int64_t n_faces,
+                 const int64_t *neighbors, const double *aol, const double *cond, int64_t n_cond,
+                 const int64_t *metaindex, int logk, const double *sources, int64_t nd, const int64_t *dnodes,
+                 const double *dheads) {
+  FVB_TRY(check_handle(h, false));
+  if (n_nodes < 0 || n_faces < 0 || nd < 0 || n_cond < 0) return set_error(FVB_ERR_BAD_INPUT, "negative size");
+  if (node_lo1 < 1 || node_hi1 > n_nodes || node_hi1 < node_lo1 - 1)
+    return set_error(FVB_ERR_BAD_INPUT, "owned node range must satisfy 1 <= lo, hi <= N");
+  if ((n_faces && (!neighbors || !aol || !cond)) || (n_nodes && !sources) || (nd && (!dnodes || !dheads)))
+    return set_error(FVB_ERR_BAD_INPUT, "null input array");
+  const int64_t n_own = node_hi1 - node_lo1 + 1;
+  if (n_own >= INT_MAX - 1 || 2 * n_faces >= INT_MAX - 1 || nd >= INT_MAX - 1)
+    return set_error(FVB_ERR_BAD_INPUT, "per-GPU part too large for 32-bit local indices; use more ranks");
+  free_problem(h);
+  cudaStream_t st = h->stream;
+  h->n_nodes = n_nodes; h->node_lo = node_lo1 - 1; h->node_hi = node_hi1; h->n_own_nodes = n_own;
+  h->n_faces = n_faces; h->n_dirichlet = nd;
+  const bool whole = (h->node_lo == 0 && h->node_hi == n_nodes);
+
+  // ---- host -> device ----------------------------------------------------------------------
+  FVB_CUDA(cudaEventRecord(h->ev[0], st));
+  int64_t *d_nb = nullptr, *d_dnodes = nullptr;
+  double *d_cond = nullptr;
+  int *d_dslot = nullptr, *d_cnt = nullptr, *d_scratch = nullptr, *d_err = nullptr;
+  int64_t *d_dsorted = nullptr, *d_refs = nullptr;
+  int *d_dsorted_slot = nullptr;
+  unsigned long long *d_noff = nullptr;
+  auto cleanup = [&]() {
+    dfree(d_nb); dfree(d_dnodes); dfree(d_cond); dfree(d_dslot); dfree(d_cnt); dfree(d_scratch); dfree(d_err);
+    dfree(d_dsorted); dfree(d_dsorted_slot); dfree(d_refs); dfree(d_noff);
+  };
+#define A_TRY(expr) do { int s__ = (expr); if (s__ != FVB_OK) { cleanup(); free_problem(h); return s__; } } while (0)
+#define A_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); free_problem(h); \
+    return set_error(FVB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+
+  A_TRY(dalloc(&d_nb, 2 * n_faces));
+  A_TRY(dalloc(&h->aol, n_faces));
+  A_TRY(dalloc(&d_cond, n_cond));
+  A_TRY(dalloc(&h->sources, n_own));
+  A_TRY(dalloc(&d_dnodes, nd));
+  A_TRY(dalloc(&h->dheads, nd));
+  A_CUDA(cudaMemcpyAsync(d_nb, neighbors, sizeof(int64_t) * 2 * (size_t)n_faces, cudaMemcpyDefault, st));
+  A_CUDA(cudaMemcpyAsync(h->aol, aol, sizeof(double) * (size_t)n_faces, cudaMemcpyDefault, st));
+  A_CUDA(cudaMemcpyAsync(d_cond, cond, sizeof(double) * (size_t)n_cond, cudaMemcpyDefault, st));
+  A_CUDA(cudaMemcpyAsync(h->sources, sources, sizeof(double) * (size_t)n_own, cudaMemcpyDefault, st));
+  A_CUDA(cudaMemcpyAsync(d_dnodes, dnodes, sizeof(int64_t) * (size_t)nd, cudaMemcpyDefault, st));
+  A_CUDA(cudaMemcpyAsync(h->dheads, dheads, sizeof(double) * (size_t)nd, cudaMemcpyDefault, st));
+  if (metaindex) {
+    A_TRY(dalloc(&h->meta, n_faces));
+    A_CUDA(cudaMemcpyAsync(h->meta, metaindex, sizeof(int64_t) * (size_t)n_faces, cudaMemcpyDefault, st));
+  }
+  A_CUDA(cudaEventRecord(h->ev[1], st));
+
+  // ---- Dirichlet table for off-rank endpoints (host: ND is small next to N) ---------------------
+  int64_t nd_sorted = 0;
+  h->row_start = 0;
+  if (!whole) {
+    std::vector<int64_t> hd((size_t)nd);
+    A_CUDA(cudaMemcpyAsync(hd.data(), d_dnodes, sizeof(int64_t) * (size_t)nd, cudaMemcpyDeviceToHost, st));
+    A_CUDA(cudaStreamSynchronize(st));
+    std::vector<std::pair<int64_t, int>> pr((size_t)nd);
+    for (int64_t k = 0; k < nd; ++k) pr[(size_t)k] = {hd[(size_t)k] - 1, (int)k};
+    std::sort(pr.begin(), pr.end());
+    std::vector<int64_t> nodes;
+    std::vector<int> slot;
+    for (size_t k = 0; k < pr.size(); ++k) {
+      if (!nodes.empty() && nodes.back() == pr[k].first) slot.back() = pr[k].second;  // last duplicate wins
+      else { nodes.push_back(pr[k].first); slot.push_back(pr[k].second); }
+    }
+    nd_sorted = (int64_t)nodes.size();
+    A_TRY(dalloc(&d_dsorted, nd_sorted));
+    A_TRY(dalloc(&d_dsorted_slot, nd_sorted));
+    A_CUDA(cudaMemcpyAsync(d_dsorted, nodes.data(), sizeof(int64_t) * nodes.size(), cudaMemcpyHostToDevice, st));
+    A_CUDA(cudaMemcpyAsync(d_dsorted_slot, slot.data(), sizeof(int) * slot.size(), cudaMemcpyHostToDevice, st));
+    A_CUDA(cudaStreamSynchronize(st));
+    int64_t below = std::lower_bound(nodes.begin(), nodes.end(), h->node_lo) - nodes.begin();
+    int64_t valid = std::lower_bound(nodes.begin(), nodes.end(), n_nodes) - std::lower_bound(nodes.begin(), nodes.end(), (int64_t)0);
+    h->row_start = h->node_lo - below;
+    h->nf_global = n_nodes - valid;
+  }
+
+  // ---- 1. node map --------------------------------------------------------------------------
+  A_TRY(dalloc(&d_err, ERR_COUNT));
+  {
+    int init[ERR_COUNT];
+    for (int &v : init) v = INT_MAX;
+    A_CUDA(cudaMemcpyAsync(d_err, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  }
+  A_TRY(dalloc(&d_dslot, n_own));
+  A_TRY(dalloc(&d_cnt, std::max(n_own, n_faces) + 2));
+  A_TRY(dalloc(&d_scratch, scan_scratch_ints(std::max(n_own, 2 * n_faces) + 1)));
+  A_CUDA(cudaMemsetAsync(d_dslot, 0xFF, sizeof(int) * (size_t)std::max<int64_t>(n_own, 1), st));
+  if (nd) {
+    k_mark_dirichlet<<<grid_for(nd), kBlock, 0, st>>>(d_dnodes, nd, n_nodes, h->node_lo, h->node_hi, h->sources,
+                                                      d_dslot, d_err);
+    h->tm.kernel_launches++;
+  }
+  int nf_local = 0;
+  if (n_own) {
+    k_free_flags<<<grid_for(n_own), kBlock, 0, st>>>(d_dslot, n_own, d_cnt);
+    h->tm.kernel_launches++;
+    exclusive_scan(d_cnt, n_own, d_cnt, d_scratch, st, &h->tm.kernel_launches);
+    A_CUDA(cudaMemcpyAsync(&nf_local, d_cnt + n_own, sizeof(int), cudaMemcpyDeviceToHost, st));
+    A_CUDA(cudaStreamSynchronize(st));
+  }
+  h->nf_local = nf_local;
+  if (whole) h->nf_global = nf_local;
+  A_TRY(dalloc(&h->nodemap, n_own));
+  A_TRY(dalloc(&h->row2node, nf_local));
+  if (n_own) {
+    k_finish_nodemap<<<grid_for(n_own), kBlock, 0, st>>>(d_dslot, d_cnt, n_own, h->nodemap, h->row2node);
+    h->tm.kernel_launches++;
+  }
+
+  // ---- 2. per-face conductance ----------------------------------------------------------------
+  A_TRY(dalloc(&h->cface, n_faces));
+  if (n_faces) {
+    k_face_conductance<<<grid_for(n_faces), kBlock, 0, st>>>(n_faces, d_cond, n_cond, h->meta, h->aol, logk,
+                                                             h->cface, d_err);
+    h->tm.kernel_launches++;
+  }
+
+  // ---- 3. adjacency ------------------------------------------------------------------------------
+  Resolver res{h->nodemap, n_nodes, h->node_lo, h->node_hi, d_dsorted, d_dsorted_slot, nd_sorted};
+  A_TRY(dalloc(&d_noff, 1));
+  A_TRY(dalloc(&h->adjptr, (int64_t)nf_local + 1));
+  unsigned long long n_off = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    A_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * ((size_t)nf_local + 1), st));
+    A_CUDA(cudaMemsetAsync(d_noff, 0, sizeof(unsigned long long), st));
+    if (n_faces) {
+      k_adjacency<0><<<grid_for(n_faces), kBlock, 0, st>>>(n_faces, d_nb, res, d_cnt, nullptr, nullptr, nullptr,
+                                                           d_noff, d_refs, nullptr, 0, nf_local, d_err);
+      h->tm.kernel_launches++;
+    }
+    A_CUDA(cudaMemcpyAsync(&n_off, d_noff, sizeof(n_off), cudaMemcpyDeviceToHost, st));
+    A_CUDA(cudaStreamSynchronize(st));
+    if (n_off == 0 || d_refs) break;
+    A_TRY(dalloc(&d_refs, (int64_t)n_off));  // second attempt records the references
+  }
+  h->n_halo = 0;
+  if (n_off) {
+    h->halo_host.resize((size_t)n_off);
+    A_CUDA(cudaMemcpy(h->halo_host.data(), d_refs, sizeof(int64_t) * (size_t)n_off, cudaMemcpyDeviceToHost));
+    std::sort(h->halo_host.begin(), h->halo_host.end());
+    h->halo_host.erase(std::unique(h->halo_host.begin(), h->halo_host.end()), h->halo_host.end());
+    h->n_halo = (int64_t)h->halo_host.size();
+    A_TRY(dalloc(&h->halo_glob, h->n_halo));
+    A_CUDA(cudaMemcpy(h->halo_glob, h->halo_host.data(), sizeof(int64_t) * (size_t)h->n_halo, cudaMemcpyHostToDevice));
+  }
+  exclusive_scan(d_cnt, nf_local, h->adjptr, d_scratch, st, &h->tm.kernel_launches);
+  int n_adj = 0;
+  A_CUDA(cudaMemcpyAsync(&n_adj, h->adjptr + nf_local, sizeof(int), cudaMemcpyDeviceToHost, st));
+  A_CUDA(cudaStreamSynchronize(st));
+  h->n_adj = n_adj;
+  A_TRY(dalloc(&h->adj_face, n_adj));
+  A_TRY(dalloc(&h->adj_col, n_adj));
+  A_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * ((size_t)nf_local + 1), st));
+  if (n_faces) {
+    k_adjacency<1><<<grid_for(n_faces), kBlock, 0, st>>>(n_faces, d_nb, res, d_cnt, h->adjptr, h->adj_face,
+                                                         h->adj_col, nullptr, nullptr, h->halo_glob, h->n_halo,
+                                                         nf_local, d_err);
+    h->tm.kernel_launches++;
+  }
+
+  // ---- 4. row structure, 5. values ------------------------------------------------------------------
+  ColKey key{nf_local, h->row_start, h->halo_glob};
+  A_TRY(dalloc(&h->rowptr, (int64_t)nf_local + 1));
+  if (nf_local) {
+    k_row_structure<<<grid_for(nf_local), kBlock, 0, st>>>(nf_local, h->adjptr, h->adj_face, h->adj_col, key, d_cnt);
+    h->tm.kernel_launches++;
+  }
+  exclusive_scan(d_cnt, nf_local, h->rowptr, d_scratch, st, &h->tm.kernel_launches);
+  int nnz = 0;
+  int herr[ERR_COUNT];
+  A_CUDA(cudaMemcpyAsync(&nnz, h->rowptr + nf_local, sizeof(int), cudaMemcpyDeviceToHost, st));
+  A_CUDA(cudaMemcpyAsync(herr, d_err, sizeof(herr), cudaMemcpyDeviceToHost, st));
+  A_CUDA(cudaStreamSynchronize(st));
+  if (herr[ERR_SRC_ON_DIRICHLET] != INT_MAX) {
+    int64_t node = 0;
+    cudaMemcpy(&node, d_dnodes + herr[ERR_SRC_ON_DIRICHLET], sizeof(int64_t), cudaMemcpyDeviceToHost);
+    cleanup(); free_problem(h);
+    return set_error(FVB_ERR_BAD_INPUT, "There cannot be a source at a Dirichlet node, but node " + std::to_string(node) +
+                                            " is a Dirichlet node where a source is located.");
+  }
+  if (herr[ERR_BAD_NODE] != INT_MAX) {
+    cleanup(); free_problem(h);
+    return set_error(FVB_ERR_BAD_INPUT, "node index out of range 1..N (neighbors or dirichletnodes entry " +
+                                            std::to_string(herr[ERR_BAD_NODE] + 1) + ")");
+  }
+  if (herr[ERR_BAD_META] != INT_MAX) {
+    cleanup(); free_problem(h);
+    return set_error(FVB_ERR_BAD_INPUT, "metaindex(" + std::to_string(herr[ERR_BAD_META] + 1) + ") is outside conductivities");
+  }
+  h->nnz = nnz;
+  A_TRY(dalloc(&h->colidx, nnz));
+  A_TRY(dalloc(&h->vals, nnz));
+  A_TRY(dalloc(&h->b, nf_local));
+  A_TRY(dalloc(&h->diag, nf_local));
+  if (nf_local) {
+    k_row_values<<<grid_for(nf_local), kBlock, 0, st>>>(nf_local, h->adjptr, h->adj_face, h->adj_col, key, h->cface,
+                                                        h->sources, h->dheads, h->row2node, h->rowptr, h->colidx,
+                                                        h->vals, h->diag, h->b, 1);
+    h->tm.kernel_launches++;
+  }
+  A_CUDA(cudaEventRecord(h->ev[2], st));
+  A_CUDA(cudaStreamSynchronize(st));
+  A_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->tm.h2d_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->tm.assemble_ms = ms;
+  cleanup();
+#undef A_TRY
+#undef A_CUDA
+  h->assembled = true;
+  h->halo_ready = (h->nranks == 1);
+  return FVB_OK;
+}
+
+int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk, const double *sources,
+                      const double *dheads) {
+  FVB_TRY(check_handle(h, true));
+  if (!cond) return set_error(FVB_ERR_BAD_INPUT, "null conductivities");
+  cudaStream_t st = h->stream;
+  double *d_cond = nullptr;
+  int *d_err = nullptr;
+  FVB_TRY(dalloc(&d_cond, n_cond));
+  FVB_TRY(dalloc(&d_err, ERR_COUNT));
+  int init[ERR_COUNT];
+  for (int &v : init) v = INT_MAX;
+  cudaMemcpyAsync(d_err, init, sizeof(init), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_cond, cond, sizeof(double) * (size_t)n_cond, cudaMemcpyDefault, st);
+  if (sources) cudaMemcpyAsync(h->sources, sources, sizeof(double) * (size_t)h->n_own_nodes, cudaMemcpyDefault, st);
+  if (dheads) cudaMemcpyAsync(h->dheads, dheads, sizeof(double) * (size_t)h->n_dirichlet, cudaMemcpyDefault, st);
+  cudaEventRecord(h->ev[1], st);
+  if (h->n_faces) {
+    k_face_conductance<<<grid_for(h->n_faces), kBlock, 0, st>>>(h->n_faces, d_cond, n_cond, h->meta, h->aol, logk,
+                                                                h->cface, d_err);
+    h->tm.kernel_launches++;
+  }
+  ColKey key{(int)h->nf_local, h->row_start, h->halo_glob};
+  if (h->nf_local) {
+    k_row_values<<<grid_for(h->nf_local), kBlock, 0, st>>>((int)h->nf_local, h->adjptr, h->adj_face, h->adj_col, key,
+                                                           h->cface, h->sources, h->dheads, h->row2node, h->rowptr,
+                                                           h->colidx, h->vals, h->diag, h->b, 0);
+    h->tm.kernel_launches++;
+  }
+  cudaEventRecord(h->ev[2], st);
+  int herr[ERR_COUNT];
+  cudaMemcpyAsync(herr, d_err, sizeof(herr), cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  dfree(d_cond); dfree(d_err);
+  if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->tm.assemble_ms = ms;
+  if (herr[ERR_BAD_META] != INT_MAX) return set_error(FVB_ERR_BAD_INPUT, "metaindex outside conductivities");
+  return FVB_OK;
+}
+
+int fvb_sizes(fvb_handle h, int64_t *nf_local, int64_t *nnz_local, int64_t *row_start, int64_t *nf_global,
+              int64_t *n_halo) {
+  FVB_TRY(check_handle(h, true));
+  if (nf_local) *nf_local = h->nf_local;
+  if (nnz_local) *nnz_local = h->nnz;
+  if (row_start) *row_start = h->row_start + 1;
+  if (nf_global) *nf_global = h->nf_global;
+  if (n_halo) *n_halo = h->n_halo;
+  return FVB_OK;
+}
+
+int fvb_get_csr(fvb_handle h, int64_t *ptr, int64_t *idx, double *val) {
+  FVB_TRY(check_handle(h, true));
+  cudaStream_t st = h->stream;
+  ColKey key{(int)h->nf_local, h->row_start, h->halo_glob};
+  // export through a bounded device staging buffer (the int64 image of colidx can be 7 GiB)
+  const int64_t chunk = 1 << 24;
+  int64_t *d_tmp = nullptr;
+  FVB_TRY(dalloc(&d_tmp, chunk));
+  if (ptr) {
+    for (int64_t o = 0; o < h->nf_local + 1; o += chunk) {
+      int64_t m = std::min(chunk, h->nf_local + 1 - o);
+      k_export_ptr<<<grid_for(m), kBlock, 0, st>>>(h->rowptr + o, m, d_tmp);
+      h->tm.kernel_launches++;
+      FVB_CUDA(cudaMemcpyAsync(ptr + o, d_tmp, sizeof(int64_t) * (size_t)m, cudaMemcpyDefault, st));
+      FVB_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  if (idx) {
+    for (int64_t o = 0; o < h->nnz; o += chunk) {
+      int64_t m = std::min(chunk, h->nnz - o);
+      k_export_cols<<<grid_for(m), kBlock, 0, st>>>(h->colidx + o, m, key, d_tmp);
+      h->tm.kernel_launches++;
+      FVB_CUDA(cudaMemcpyAsync(idx + o, d_tmp, sizeof(int64_t) * (size_t)m, cudaMemcpyDefault, st));
+      FVB_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  dfree(d_tmp);
+  if (val) FVB_CUDA(cudaMemcpy(val, h->vals, sizeof(double) * (size_t)h->nnz, cudaMemcpyDefault));
+  return FVB_OK;
+}
+
+int fvb_get_b(fvb_handle h, double *b) {
+  FVB_TRY(check_handle(h, true));
+  FVB_CUDA(cudaMemcpy(b, h->b, sizeof(double) * (size_t)h->nf_local, cudaMemcpyDefault));
+  return FVB_OK;
+}
+int fvb_get_diag(fvb_handle h, double *d) {
+  FVB_TRY(check_handle(h, true));
+  FVB_CUDA(cudaMemcpy(d, h->diag, sizeof(double) * (size_t)h->nf_local, cudaMemcpyDefault));
+  return FVB_OK;
+}
+
+static int export_nodemap(fvb_handle h, uint8_t *freenode, int64_t *n2f) {
+  FVB_TRY(check_handle(h, true));
+  const int64_t n = h->n_own_nodes;
+  uint8_t *d_f = nullptr;
+  int64_t *d_m = nullptr;
+  if (freenode) FVB_TRY(dalloc(&d_f, n));
+  if (n2f) FVB_TRY(dalloc(&d_m, n));
+  if (n) {
+    k_export_nodemap<<<grid_for(n), kBlock, 0, h->stream>>>(h->nodemap, n, h->row_start, d_f, d_m);
+    h->tm.kernel_launches++;
+  }
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess && freenode) e = cudaMemcpy(freenode, d_f, (size_t)n, cudaMemcpyDefault);
+  if (e == cudaSuccess && n2f) e = cudaMemcpy(n2f, d_m, sizeof(int64_t) * (size_t)n, cudaMemcpyDefault);
+  dfree(d_f); dfree(d_m);
+  if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+  return FVB_OK;
+}
+int fvb_get_freenode(fvb_handle h, uint8_t *freenode) { return export_nodemap(h, freenode, nullptr); }
+int fvb_get_nodei2freenodei(fvb_handle h, int64_t *map) { return export_nodemap(h, nullptr, map); }
+
+int fvb_get_halo_cols(fvb_handle h, int64_t *cols) {
+  FVB_TRY(check_handle(h, true));
+  for (int64_t k = 0; k < h->n_halo; ++k) cols[k] = h->halo_host[(size_t)k] + 1;
+  return FVB_OK;
+}
+
+int fvb_set_halo_plan(fvb_handle h, int n_peers, const int32_t *peer_ranks, const int64_t *send_counts,
+                      const int32_t *send_rows, const int64_t *recv_counts) {
+  FVB_TRY(check_handle(h, true));
+  if (n_peers < 0) return set_error(FVB_ERR_BAD_INPUT, "negative peer count");
+  int64_t ns = 0, nr = 0;
+  for (int p = 0; p < n_peers; ++p) { ns += send_counts[p]; nr += recv_counts[p]; }
+  if (nr != h->n_halo) return set_error(FVB_ERR_BAD_INPUT, "recv counts do not add up to the halo size");
+  std::vector<int32_t> rows(send_rows, send_rows + ns);
+  for (int32_t r : rows)
+    if (r < 0 || r >= h->nf_local) return set_error(FVB_ERR_BAD_INPUT, "send row outside the owned range");
+  h->peers.assign(peer_ranks, peer_ranks + n_peers);
+  h->send_counts.assign(send_counts, send_counts + n_peers);
+  h->recv_counts.assign(recv_counts, recv_counts + n_peers);
+  dfree(h->send_rows); dfree(h->sendbuf);
+  FVB_TRY(dalloc(&h->send_rows, ns));
+  FVB_TRY(dalloc(&h->sendbuf, ns));
+  FVB_CUDA(cudaMemcpy(h->send_rows, rows.data(), sizeof(int32_t) * (size_t)ns, cudaMemcpyHostToDevice));
+  h->n_send = ns;
+  h->halo_ready = true;
+  return FVB_OK;
+}
+
+int fvb_solve(fvb_handle h, double rtol, int64_t maxiter, const double *x0_free, double *head_nodes, double *x_free,
+              int64_t *iters, int *converged, double *resnorm_hist, int64_t hist_cap) {
+  FVB_TRY(check_handle(h, true));
+  if (maxiter < 0) return set_error(FVB_ERR_BAD_INPUT, "maxiter must be >= 0");
+  FVB_TRY(ensure_workspace(h));
+  cudaStream_t st = h->stream;
+  const int64_t n = h->nf_local;
+  FVB_CUDA(cudaEventRecord(h->ev[3], st));
+  if (x0_free) FVB_CUDA(cudaMemcpyAsync(h->x, x0_free, sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
+  int64_t it = 0;
+  int conv = 0;
+  double *saveD = h->Dvec;  // the steady operator is A itself
+  FVB_TRY(pcg_run(h, h->b, x0_free != nullptr, 0.0, rtol, maxiter, &it, &conv));
+  h->Dvec = saveD;
+  FVB_CUDA(cudaEventRecord(h->ev[4], st));
+  if (head_nodes) {
+    double *d_head = nullptr;
+    FVB_TRY(dalloc(&d_head, h->n_own_nodes));
+    if (h->n_own_nodes) {
+      k_scatter_heads<<<grid_for(h->n_own_nodes), kBlock, 0, st>>>(h->nodemap, h->n_own_nodes, h->x, h->dheads, d_head);
+      h->tm.kernel_launches++;
+    }
+    cudaError_t e = cudaMemcpyAsync(head_nodes, d_head, sizeof(double) * (size_t)h->n_own_nodes, cudaMemcpyDefault, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    dfree(d_head);
+    if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (x_free) FVB_CUDA(cudaMemcpyAsync(x_free, h->x, sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
+  if (resnorm_hist && hist_cap > 0) {
+    int64_t m = std::min<int64_t>(std::min<int64_t>(it, hist_cap), h->hist_cap);
+    if (m > 0) FVB_CUDA(cudaMemcpyAsync(resnorm_hist, h->hist, sizeof(double) * (size_t)m, cudaMemcpyDefault, st));
+  }
+  FVB_CUDA(cudaEventRecord(h->ev[5], st));
+  FVB_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->tm.solve_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->tm.d2h_ms = ms;
+  if (iters) *iters = it;
+  if (converged) *converged = conv;
+  return FVB_OK;
+}
+
+int fvb_spmv(fvb_handle h, double alpha, const double *x, double beta, double *y) {
+  FVB_TRY(check_handle(h, true));
+  FVB_TRY(ensure_workspace(h));
+  cudaStream_t st = h->stream;
+  const int64_t n = h->nf_local;
+  if (!h->yio) FVB_TRY(dalloc(&h->yio, n));
+  FVB_CUDA(cudaMemcpyAsync(h->u, x, sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
+  if (beta != 0.0) FVB_CUDA(cudaMemcpyAsync(h->yio, y, sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
+  FVB_TRY(launch_spmv(h, h->u, h->c, 0.0, false));
+  k_axpby<<<vgrid(h, n), kBlock, 0, st>>>(n, alpha, h->c, beta, h->yio);
+  h->tm.kernel_launches++;
+  FVB_CUDA(cudaMemcpyAsync(y, h->yio, sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
+  FVB_CUDA(cudaStreamSynchronize(st));
+  return FVB_OK;
+}
+
+// ---- transient --------------------------------------------------------------------------------------
+int fvb_vec_upload(fvb_handle h, int slot, const double *host) {
+  FVB_TRY(check_handle(h, true));
+  FVB_TRY(ensure_slot(h, slot));
+  FVB_CUDA(cudaMemcpyAsync(h->slots[slot], host, sizeof(double) * (size_t)h->nf_local, cudaMemcpyDefault, h->stream));
+  FVB_CUDA(cudaStreamSynchronize(h->stream));
+  return FVB_OK;
+}
+int fvb_vec_download(fvb_handle h, int slot, double *host) {
+  FVB_TRY(check_handle(h, true));
+  FVB_TRY(ensure_slot(h, slot));
+  FVB_CUDA(cudaMemcpyAsync(host, h->slots[slot], sizeof(double) * (size_t)h->nf_local, cudaMemcpyDefault, h->stream));
+  FVB_CUDA(cudaStreamSynchronize(h->stream));
+  return FVB_OK;
+}
+int fvb_vec_copy(fvb_handle h, int dst, int src) {
+  FVB_TRY(check_handle(h, true));
+  FVB_TRY(ensure_slot(h, dst));
+  FVB_TRY(ensure_slot(h, src));
+  if (dst != src)
+    FVB_CUDA(cudaMemcpyAsync(h->slots[dst], h->slots[src], sizeof(double) * (size_t)h->nf_local,
+                             cudaMemcpyDeviceToDevice, h->stream));
+  return FVB_OK;
+}
+int fvb_vec_load_b(fvb_handle h, int slot) {
+  FVB_TRY(check_handle(h, true));
+  FVB_TRY(ensure_slot(h, slot));
+  FVB_CUDA(cudaMemcpyAsync(h->slots[slot], h->b, sizeof(double) * (size_t)h->nf_local, cudaMemcpyDeviceToDevice, h->stream));
+  return FVB_OK;
+}
+int fvb_vec_diffnorm(fvb_handle h, int a, int b, double *out) {
+  FVB_TRY(check_handle(h, true));
+  FVB_TRY(ensure_slot(h, a));
+  FVB_TRY(ensure_slot(h, b));
+  FVB_TRY(ensure_workspace(h));
+  const int64_t n = h->nf_local;
+  k_diffnorm2<<<vgrid(h, n), kBlock, 0, h->stream>>>(n, h->slots[a], h->slots[b], h->partials, h->ticket, h->scal->red);
+  h->tm.kernel_launches++;
+  FVB_TRY(allreduce_sum(h, h->scal->red, 1));
+  double s = 0;
+  FVB_CUDA(cudaMemcpyAsync(&s, h->scal->red, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  FVB_CUDA(cudaStreamSynchronize(h->stream));
+  *out = std::sqrt(s);
+  return FVB_OK;
+}
+int fvb_set_storage(fvb_handle h, double Ss, const double *volumes) {
+  FVB_TRY(check_handle(h, true));
+  if (!volumes) { dfree(h->Dvec); return FVB_OK; }
+  double *d_vol = nullptr;
+  FVB_TRY(dalloc(&d_vol, h->n_own_nodes));
+  if (!h->Dvec) FVB_TRY(dalloc(&h->Dvec, h->nf_local));
+  cudaMemcpyAsync(d_vol, volumes, sizeof(double) * (size_t)h->n_own_nodes, cudaMemcpyDefault, h->stream);
+  k_make_D<<<vgrid(h, h->nf_local), kBlock, 0, h->stream>>>(h->nf_local, h->row2node, d_vol, Ss, h->Dvec);
+  h->tm.kernel_launches++;
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  dfree(d_vol);
+  if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+  return FVB_OK;
+}
+int fvb_step(fvb_handle h, int rhs_slot, int u_slot, double dt, int out_slot, int adjoint, double rtol,
+             int64_t maxiter, int64_t *iters, int *converged) {
+  FVB_TRY(check_handle(h, true));
+  if (!(dt > 0)) return set_error(FVB_ERR_BAD_INPUT, "time step must be positive");
+  FVB_TRY(ensure_slot(h, rhs_slot));
+  FVB_TRY(ensure_slot(h, u_slot));
+  FVB_TRY(ensure_slot(h, out_slot));
+  FVB_TRY(ensure_workspace(h));
+  const int64_t n = h->nf_local;
+  cudaStream_t st = h->stream;
+  const int vg = vgrid(h, n);
+  const double sigma = 1.0 / dt;
+  if (!adjoint) {
+    k_axpby_D<<<vg, kBlock, 0, st>>>(n, h->slots[rhs_slot], h->slots[u_slot], h->Dvec, sigma, h->rhs);
+    FVB_CUDA(cudaMemcpyAsync(h->x, h->slots[u_slot], sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  } else {
+    k_axpby_D<<<vg, kBlock, 0, st>>>(n, h->slots[rhs_slot], h->slots[u_slot], nullptr, sigma, h->rhs);
+    k_scale_D<<<vg, kBlock, 0, st>>>(n, h->slots[u_slot], h->Dvec, 0, h->x);
+    h->tm.kernel_launches++;
+  }
+  h->tm.kernel_launches++;
+  FVB_TRY(pcg_run(h, h->rhs, true, sigma, rtol, maxiter, iters, converged));
+  if (!adjoint) {
+    FVB_CUDA(cudaMemcpyAsync(h->slots[out_slot], h->x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  } else {
+    k_scale_D<<<vg, kBlock, 0, st>>>(n, h->x, h->Dvec, 1, h->slots[out_slot]);
+    h->tm.kernel_launches++;
+  }
+  return FVB_OK;
+}
+int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes) {
+  FVB_TRY(check_handle(h, true));
+  FVB_TRY(ensure_slot(h, slot));
+  double *d_head = nullptr;
+  FVB_TRY(dalloc(&d_head, h->n_own_nodes));
+  if (h->n_own_nodes) {
+    k_scatter_heads<<<grid_for(h->n_own_nodes), kBlock, 0, h->stream>>>(h->nodemap, h->n_own_nodes, h->slots[slot],
+                                                                        h->dheads, d_head);
+    h->tm.kernel_launches++;
+  }
+  cudaError_t e = cudaMemcpyAsync(head_nodes, d_head, sizeof(double) * (size_t)h->n_own_nodes, cudaMemcpyDefault, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  dfree(d_head);
+  if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+  return FVB_OK;
+}
+
+// ---- measurement ---------------------------------------------------------------------------------------
+int fvb_time_spmv(fvb_handle h, int warmup, int reps, double *ms_avg) {
+  FVB_TRY(check_handle(h, true));
+  FVB_TRY(ensure_workspace(h));
+  if (reps < 1) return set_error(FVB_ERR_BAD_INPUT, "reps must be >= 1");
+  const int64_t n = h->nf_local;
+  cudaStream_t st = h->stream;
+  // x = diag(A) (any resident non-trivial vector will do; contents do not affect traffic)
+  FVB_CUDA(cudaMemcpyAsync(h->u, h->diag, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < warmup; ++i) FVB_TRY(launch_spmv(h, h->u, h->c, 0.0, false));
+  FVB_CUDA(cudaEventRecord(h->ev[3], st));
+  for (int i = 0; i < reps; ++i) FVB_TRY(launch_spmv(h, h->u, h->c, 0.0, false));
+  FVB_CUDA(cudaEventRecord(h->ev[4], st));
+  FVB_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  FVB_CUDA(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]));
+  *ms_avg = (double)ms / reps;
+  return FVB_OK;
+}
+
+int fvb_get_timings(fvb_handle h, fvb_timings *out) {
+  if (!h || !out) return set_error(FVB_ERR_BAD_INPUT, "null argument");
+  *out = h->tm;
+  return FVB_OK;
+}
+
+int fvb_sync(fvb_handle h) {
+  FVB_TRY(check_handle(h, false));
+  FVB_CUDA(cudaStreamSynchronize(h->stream));
+  return FVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,152 @@
+// pcg.cuh -- fused vector kernels of the Jacobi-preconditioned CG.
+// Recurrence, naming and stopping rule follow IterativeSolvers.cg 0.8.1, the solver the
+// reference calls at src/FiniteVolume.jl:161 and src/transient.jl:52,55 (Pl = Jacobi here,
+// per north_star, instead of Ruge-Stueben AMG):
+//     c = Pl \ r ; rho_prev = rho ; rho = c.r ; beta = rho/rho_prev ; u = c + beta u
+//     c = A u ; alpha = rho / u.c ; x += alpha u ; r -= alpha c ; residual = ||r||
+//     stop when residual <= tol * ||r0|| or iteration == maxiter
+// One iteration = three launches: k_update_u, k_spmv<DOT>, k_update_xr.  All scalars stay
+// in device memory (PcgScal); every kernel returns at once when scal->done is set, so the
+// host can enqueue iterations in batches without synchronising.
+#pragma once
+#include "common.cuh"
+#include "reduce.cuh"
+
+namespace fvb {
+
+__device__ __forceinline__ void pcg_finish_init(PcgScal *s, double rho0, double rr0) {
+  s->rho = rho0;
+  s->rho_prev = 1.0;
+  s->resid0 = sqrt(rr0);
+  s->resid = s->resid0;
+  s->reltol = s->resid0 * s->tol;
+  s->iter = 0;
+  s->converged = s->resid0 <= s->reltol;
+  s->done = s->converged || s->maxiter <= 0;
+}
+
+__device__ __forceinline__ void pcg_finish_iter(PcgScal *s, double rho_new, double rr, double *hist) {
+  s->rho_prev = s->rho;
+  s->rho = rho_new;
+  const double resid = sqrt(rr);
+  s->resid = resid;
+  if (s->iter < s->hist_cap) hist[s->iter] = resid;
+  s->iter += 1;
+  if (resid <= s->reltol) { s->done = 1; s->converged = 1; }
+  else if (s->iter >= s->maxiter) s->done = 1;
+}
+
+// single-thread kernels used after the NCCL all-reduce in multi-rank runs
+__global__ void k_fin_init(PcgScal *s) { pcg_finish_init(s, s->red[0], s->red[1]); }
+__global__ void k_fin_uc(PcgScal *s) { if (!s->done) s->uc = s->red[0]; }
+__global__ void k_fin_iter(PcgScal *s, double *hist) { if (!s->done) pcg_finish_iter(s, s->red[0], s->red[1], hist); }
+
+__global__ void k_set_scal(PcgScal *s, double tol, long long maxiter, long long hist_cap) {
+  s->tol = tol; s->maxiter = maxiter; s->hist_cap = hist_cap;
+  s->done = 0; s->converged = 0; s->iter = 0;
+  s->rho = 0; s->rho_prev = 1; s->uc = 0; s->resid = 0; s->resid0 = 0; s->reltol = 0;
+}
+
+// dinv = 1 / (diag + sigma * D)   (Jacobi preconditioner of A + sigma*D)
+__global__ void k_make_dinv(int64_t n, const double *__restrict__ diag, const double *__restrict__ Dvec,
+                            double sigma, double *__restrict__ dinv) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dinv[i] = 1.0 / (diag[i] + sigma * (Dvec ? Dvec[i] : 1.0));
+}
+
+// r = rhs - c (c = A x0, when have_x0) or r = rhs, x = 0; sums (dinv r).r and r.r
+__global__ void __launch_bounds__(kBlock)
+k_pcg_init(int64_t n, const double *__restrict__ rhs, const double *__restrict__ c, int have_x0,
+           const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r,
+           double *partials, unsigned int *ticket, PcgScal *scal, int finalize_mode) {
+  double s0 = 0.0, s1 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double ri;
+    if (have_x0) ri = rhs[i] - c[i];
+    else { ri = rhs[i]; x[i] = 0.0; }
+    r[i] = ri;
+    s0 += dinv[i] * ri * ri;
+    s1 += ri * ri;
+  }
+  s0 = block_sum(s0);
+  s1 = block_sum(s1);
+  double t0, t1;
+  if (last_block_sum2(s0, s1, partials, ticket, &t0, &t1)) {
+    scal->red[0] = t0; scal->red[1] = t1;
+    if (finalize_mode == 1) pcg_finish_init(scal, t0, t1);
+  }
+}
+
+// u = dinv .* r + beta * u
+__global__ void __launch_bounds__(kBlock)
+k_update_u(int64_t n, const double *__restrict__ dinv, const double *__restrict__ r, double *__restrict__ u,
+           const PcgScal *__restrict__ scal) {
+  if (scal->done) return;
+  const double beta = scal->iter == 0 ? 0.0 : scal->rho / scal->rho_prev;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    u[i] = dinv[i] * r[i] + beta * u[i];
+}
+
+// x += alpha u ; r -= alpha c ; sums (dinv r).r and r.r ; last block closes the iteration
+__global__ void __launch_bounds__(kBlock)
+k_update_xr(int64_t n, const double *__restrict__ u, const double *__restrict__ c,
+            const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r,
+            double *partials, unsigned int *ticket, PcgScal *scal, double *hist, int finalize_mode) {
+  if (scal->done) return;
+  const double alpha = scal->rho / scal->uc;
+  double s0 = 0.0, s1 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * u[i];
+    const double ri = r[i] - alpha * c[i];
+    r[i] = ri;
+    s0 += dinv[i] * ri * ri;
+    s1 += ri * ri;
+  }
+  s0 = block_sum(s0);
+  s1 = block_sum(s1);
+  double t0, t1;
+  if (last_block_sum2(s0, s1, partials, ticket, &t0, &t1)) {
+    scal->red[0] = t0; scal->red[1] = t1;
+    if (finalize_mode == 1) pcg_finish_iter(scal, t0, t1, hist);
+  }
+}
+
+// ---- small vector helpers for the transient path (src/transient.jl:71, :81) ---------------
+// out = b + scale * (D ? D .* u : u)
+__global__ void k_axpby_D(int64_t n, const double *__restrict__ b, const double *__restrict__ u,
+                          const double *__restrict__ Dvec, double scale, double *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = b[i] + scale * (Dvec ? Dvec[i] * u[i] : u[i]);
+}
+// out = D ? (mul ? D .* v : v ./ D) : v
+__global__ void k_scale_D(int64_t n, const double *__restrict__ v, const double *__restrict__ Dvec, int mul,
+                          double *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = Dvec ? (mul ? Dvec[i] * v[i] : v[i] / Dvec[i]) : v[i];
+}
+// y = alpha * c + beta * y
+__global__ void k_axpby(int64_t n, double alpha, const double *__restrict__ c, double beta, double *__restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = beta == 0.0 ? alpha * c[i] : alpha * c[i] + beta * y[i];
+}
+// sum (a-b)^2 -> red[0]
+__global__ void __launch_bounds__(kBlock)
+k_diffnorm2(int64_t n, const double *__restrict__ a, const double *__restrict__ b, double *partials,
+            unsigned int *ticket, double *out) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double d = a[i] - b[i];
+    s += d * d;
+  }
+  s = block_sum(s);
+  double t;
+  if (last_block_sum1(s, partials, ticket, &t)) *out = t;
+}
+// D_r = Ss * volumes[node(r)]
+__global__ void k_make_D(int64_t nf, const int *__restrict__ row2node, const double *__restrict__ vol, double Ss,
+                         double *__restrict__ D) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += (int64_t)gridDim.x * blockDim.x)
+    D[i] = Ss * vol[row2node[i]];
+}
+
+}  // namespace fvb

@@ -1,0 +1,100 @@
+"""One-rank-per-GPU plumbing for slab-partitioned problems.
+
+Only setup-time, host-side logic lives here: choosing contiguous node ranges, exchanging the
+NCCL unique id, and turning each rank's list of referenced off-rank columns into the
+send/receive lists the library needs.  It uses torch.distributed collectives on small host
+objects, so it runs unchanged on gloo (CPU tests) and on a NCCL job.  The per-iteration
+traffic (halo planes, CG scalars) is NCCL inside libfvb200.so, not here.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def slab_planes(n1: int, nranks: int, dirichlet_end_planes: bool = True):
+    """Split x-planes 1..n1 into `nranks` contiguous slabs, balancing FREE planes: with the
+    usual left/right Dirichlet faces (examples/box_model/ex.jl:27-37) planes 1 and n1 carry no
+    unknowns, so the end ranks take one plane more.  Returns [(p_lo, p_hi)] 1-based inclusive."""
+    if nranks < 1 or n1 < nranks:
+        raise ValueError("need at least one plane per rank")
+    fixed = 2 if (dirichlet_end_planes and n1 >= 2 + nranks) else 0
+    free = n1 - fixed
+    base, extra = divmod(free, nranks)
+    counts = [base + (1 if r < extra else 0) for r in range(nranks)]
+    if fixed:
+        counts[0] += 1
+        counts[-1] += 1
+    out, lo = [], 1
+    for c in counts:
+        out.append((lo, lo + c - 1))
+        lo += c
+    assert lo == n1 + 1
+    return out
+
+
+def node_range_of_planes(planes, n2, n3):
+    """Planes (p_lo, p_hi) -> owned node range (lo, hi), 1-based inclusive (src/grid.jl:60)."""
+    return (planes[0] - 1) * n2 * n3 + 1, planes[1] * n2 * n3
+
+
+def halo_plan_from_ranges(rank, row_ranges, halo_cols_by_rank):
+    """Pure function (no communication): given every rank's (row_start, nf_local) (1-based
+    start) and every rank's ascending list of referenced off-rank global columns, return for
+    `rank`: peers, send_counts, send_rows (0-based local), recv_counts.  Halo entries arrive
+    grouped by owner in ascending rank order, which is ascending column order because ranks
+    own ascending row ranges."""
+    starts = np.array([r[0] for r in row_ranges], np.int64)
+    ends = starts + np.array([r[1] for r in row_ranges], np.int64)  # exclusive
+
+    def owner(cols):
+        o = np.searchsorted(starts, cols, side="right") - 1
+        if cols.size and (np.any(o < 0) or np.any(cols >= ends[o])):
+            raise ValueError("halo column outside every rank's row range")
+        return o
+
+    mine = np.asarray(halo_cols_by_rank[rank], np.int64)
+    if mine.size and np.any(np.diff(mine) <= 0):
+        raise ValueError("halo columns must be strictly ascending")
+    own_mine = owner(mine)
+    if np.any(own_mine == rank):
+        raise ValueError("a halo column is owned by the requesting rank")
+    send = {}
+    for q, cols in enumerate(halo_cols_by_rank):
+        if q == rank:
+            continue
+        cols = np.asarray(cols, np.int64)
+        sel = cols[owner(cols) == rank]
+        if sel.size:
+            send[q] = (sel - starts[rank]).astype(np.int32)
+    recv = {int(p): int(np.count_nonzero(own_mine == p)) for p in np.unique(own_mine)}
+    peers = sorted(set(send) | set(recv))
+    send_counts = [int(send[p].size) if p in send else 0 for p in peers]
+    recv_counts = [recv.get(p, 0) for p in peers]
+    send_rows = np.concatenate([send[p] for p in peers if p in send]) if send else np.empty(0, np.int32)
+    return peers, send_counts, send_rows, recv_counts
+
+
+def exchange_halo_plan(system, group=None):
+    """Collective: gather row ranges and halo lists over torch.distributed and install the plan."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    s = system.sizes()
+    mine = (int(s["row_start"]), int(s["nf_local"]), system.halo_cols())
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    plan = halo_plan_from_ranges(rank, [(g[0], g[1]) for g in gathered], [g[2] for g in gathered])
+    system.set_halo_plan(*plan)
+    return plan
+
+
+def init_comm(system, group=None):
+    """Collective: rank 0 creates the NCCL unique id, everyone joins (fvb_comm_init)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return
+    box = [type(system).unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    system.comm_init(world, rank, box[0])

@@ -1,0 +1,244 @@
+"""Transient / adjoint drivers mirroring src/transient.jl.
+
+The step controller (step doubling, rejection, growth) is host logic in the reference and
+stays host logic here; it is restated from src/transient.jl:78-154 function by function.
+What changed is where vectors live: every state vector is a *device-resident slot* of the
+System, a backward-Euler solve is one `fvb_step` call, and the controller only ever pulls
+one scalar (||onestep - twostep||, :81) across PCIe per attempted step.
+
+Linear algebra of one step.  The reference scales rows, At = D^-1 A with D = Ss*volumes
+(scalebyvolume!, :7-22), and solves the non-symmetric (At + I/dt) u+ = D^-1 b + u/dt (:71-73)
+by CG with an AMG fallback (:50-58).  We solve the equivalent SPD system
+(A + D/dt) u+ = b + D u/dt with Jacobi-PCG; the adjoint step
+(At^T + I/dt) g+ = f + g/dt (:193,:203) becomes (A + D/dt) w = f + g/dt, g+ = D w.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .api import DEFAULT_MAXITER, SQRT_EPS, System
+
+
+class _Pool:
+    """Hands out the FVB_NSLOT device vector slots; a DVec returns its slot when dropped."""
+
+    def __init__(self, system: System, reserved=()):
+        self.sys = system
+        self.free = [s for s in range(_lib.NSLOT) if s not in reserved]
+
+    def new(self):
+        if not self.free:
+            raise RuntimeError("out of device vector slots")
+        return DVec(self, self.free.pop())
+
+
+class DVec:
+    def __init__(self, pool, slot):
+        self.pool, self.slot = pool, slot
+
+    def __del__(self):
+        try:
+            self.pool.free.append(self.slot)
+        except Exception:
+            pass
+
+
+class DeviceStepper:
+    """backwardeuleronestep! (src/transient.jl:65-76) on device slots."""
+
+    def __init__(self, system: System, getb, adjoint=False, rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER):
+        self.sys, self.getb, self.adjoint, self.rtol, self.maxiter = system, getb, adjoint, rtol, maxiter
+        self.pool = _Pool(system, reserved=(0,))
+        self.linear_solves = 0
+        self.cg_iterations = 0
+        self._b_key = object()
+
+    def _load_b(self, t):
+        b = self.getb(t)
+        if b is None:  # constant assembled b already resident
+            if self._b_key is not None:
+                self.sys.vec_load_b(0)
+                self._b_key = None
+        else:
+            self.sys.vec_upload(0, b)
+            self._b_key = object()
+
+    def onestep(self, u: DVec, t, dt) -> DVec:
+        if dt <= 0:
+            raise ValueError("time step must be positive")  # src/transient.jl:68-70
+        self._load_b(t)
+        out = self.pool.new()
+        it, _ = self.sys.step(0, u.slot, dt, out.slot, adjoint=self.adjoint, rtol=self.rtol, maxiter=self.maxiter)
+        self.linear_solves += 1
+        self.cg_iterations += it
+        return out
+
+    def diffnorm(self, a: DVec, b: DVec) -> float:
+        return self.sys.vec_diffnorm(a.slot, b.slot)
+
+    def upload(self, v) -> DVec:
+        d = self.pool.new()
+        self.sys.vec_upload(d.slot, v)
+        return d
+
+    def download(self, d: DVec):
+        return self.sys.vec_download(d.slot)
+
+
+class HostStepper:
+    """The reference's pluggable `linearsolver(A, rhs, x0)` hook (src/transient.jl:136, used
+    with `A \\ b` in test/ode.jl:36) for a user-supplied matrix.  Only the controller runs
+    here; the solve is entirely the caller's function -- there is no built-in CPU solver."""
+
+    def __init__(self, A, getb, linearsolver):
+        if linearsolver is None:
+            raise RuntimeError("a generic (non finite-volume) matrix needs an explicit linearsolver(A, rhs, x0); "
+                               "finitevolume.jl_b200 has no CPU solver to fall back to")
+        self.A, self.getb, self.linearsolver = A, getb, linearsolver
+        self.linear_solves = 0
+
+    def onestep(self, u, t, dt):
+        if dt <= 0:
+            raise ValueError("time step must be positive")
+        rhs = self.getb(t) + u / dt
+        n = self.A.shape[0]
+        try:
+            import scipy.sparse as sp
+            shifted = self.A + (sp.identity(n, format="csr") / dt if sp.issparse(self.A) else np.eye(n) / dt)
+        except ImportError:  # dense only
+            shifted = self.A + np.eye(n) / dt
+        self.linear_solves += 1
+        return np.asarray(self.linearsolver(shifted, rhs, u)).reshape(-1)
+
+    def diffnorm(self, a, b):
+        return float(np.linalg.norm(a - b))
+
+    def upload(self, v):
+        return np.array(v, dtype=np.float64)
+
+    def download(self, d):
+        return d
+
+
+# ---- the controller: src/transient.jl:78-154 ----------------------------------------------------------
+def backwardeulertwostep(S, u_k, t, dt, atol, onestep=None):
+    """src/transient.jl:78-87."""
+    if onestep is None:
+        onestep = S.onestep(u_k, t, dt)
+    twostep1 = S.onestep(u_k, t, 0.5 * dt)
+    twostep = S.onestep(twostep1, t + 0.5 * dt, 0.5 * dt)
+    err = S.diffnorm(onestep, twostep)
+    if err < atol:
+        return twostep, dt, err < atol / 4
+    return twostep1, 0.5 * dt, False
+
+
+def adaptivebackwardeulerstep(S, u_k, t, dt, atol, callback):
+    """src/transient.jl:89-121."""
+    callback(t, dt)
+    u_new, laststeptime, increasestepsize = backwardeulertwostep(S, u_k, t, dt, atol)
+    if laststeptime < dt:
+        laststepfailed = True
+        elapsedtime = 0.0
+        u_elapsedtime = u_k
+        targetdt = laststeptime
+        while elapsedtime < dt:
+            callback(t, dt)
+            if laststepfailed:
+                u_new, laststeptime, increasestepsize = backwardeulertwostep(S, u_elapsedtime, t + elapsedtime, targetdt,
+                                                                             atol, u_new)
+            else:
+                u_new, laststeptime, increasestepsize = backwardeulertwostep(S, u_elapsedtime, t + elapsedtime, targetdt,
+                                                                             atol)
+            if laststeptime == targetdt:
+                elapsedtime += laststeptime
+                u_elapsedtime = u_new
+                if increasestepsize:
+                    targetdt = 2 * laststeptime
+                laststepfailed = False
+            elif laststeptime < targetdt:
+                targetdt = laststeptime
+                laststepfailed = True
+            else:
+                raise RuntimeError("Code is broken -- laststeptime should never be greater than targetdt")
+            targetdt = min(targetdt, dt - elapsedtime)
+    return u_new, laststeptime, increasestepsize
+
+
+def fixedbackwardeulerstep(S, u_k, t, dt, atol, callback):
+    """src/transient.jl:130-134."""
+    callback(t, dt)
+    return S.onestep(u_k, t, dt), dt, False
+
+
+def _integrate(S, u0, dt0, t0, tfinal, stepper, atol, callback, keep):
+    """src/transient.jl:136-154.  `keep(dvec)` converts an accepted state for storage."""
+    u = S.upload(u0)
+    us = [keep(u)]
+    ts = [t0]
+    dt = min(dt0, tfinal - t0)
+    while ts[-1] < tfinal:
+        u, laststeptime, increasestepsize = stepper(S, u, ts[-1], dt, atol, callback)
+        us.append(keep(u))
+        ts.append(ts[-1] + dt)
+        dt = min(tfinal - ts[-1], 2 * laststeptime) if increasestepsize else min(tfinal - ts[-1], laststeptime)
+    return us, ts
+
+
+def backwardeulerintegrate_generic(u0, A, b, dt0, t0, tfinal, stepper=adaptivebackwardeulerstep, linearsolver=None,
+                                   atol=1e-4, callback=lambda t, dt: None):
+    """backwardeulerintegrate(u0, A, b|getb, dt0, t0, tfinal; ...) for a caller-supplied matrix
+    (src/transient.jl:123-128, :136-154): controller here, solves in the caller's linearsolver."""
+    getb = b if callable(b) else (lambda t, _b=np.asarray(b, dtype=np.float64): _b)
+    S = HostStepper(A, getb, linearsolver)
+    return _integrate(S, u0, dt0, t0, tfinal, stepper, atol, callback, keep=lambda v: np.array(v))
+
+
+def backwardeulerintegrate(u0, tspan, Ss, volumes, neighbors, areasoverlengths, conductivities, sources,
+                           dirichletnodes, dirichletheads, metaindex=None, logtransformconductivity=False, *,
+                           dt0=1.0, stepper=adaptivebackwardeulerstep, atol=1e-4, callback=lambda t, dt: None,
+                           getb=None, rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER, device=0, stats=None):
+    """Model-level entry, src/transient.jl:156-174 -> (us, ts); every us[i] is a length-N head
+    vector (free rows scattered, Dirichlet heads filled in, :172).
+
+    getb(t), when given, must return the UNSCALED right-hand side b(t) on the free rows (the
+    reference's getb returns D^-1 b; multiply by Ss*volumes[free] to convert)."""
+    u0 = np.asarray(u0, np.float64)
+    sysm = System(device).assemble(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
+                                   metaindex, logtransformconductivity)
+    try:
+        sysm.set_storage(float(Ss), np.asarray(volumes, np.float64))
+        freenode = sysm.freenode()
+        S = DeviceStepper(sysm, getb if getb is not None else (lambda t: None), adjoint=False, rtol=rtol, maxiter=maxiter)
+        us, ts = _integrate(S, u0[freenode], dt0, tspan[0], tspan[1], stepper, atol, callback,
+                            keep=lambda d: sysm.vec_to_nodes(d.slot))
+        # the initial entry is the caller's u0 restricted to free nodes + Dirichlet heads (:170-172)
+        if stats is not None:
+            stats.update(linear_solves=S.linear_solves, cg_iterations=S.cg_iterations, steps=len(ts) - 1)
+        return us, ts
+    finally:
+        sysm.close()
+
+
+def adjointintegrate(getdgdu, tspan, Ss, volumes, neighbors, areasoverlengths, conductivities, sources,
+                     dirichletnodes, dirichletheads, metaindex=None, logtransformconductivity=False, *,
+                     dt0=1.0, stepper=adaptivebackwardeulerstep, atol=1e-4, callback=lambda t, dt: None,
+                     rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER, device=0, stats=None):
+    """src/transient.jl:188-205 -> (lambdas, ts_lambda): integrates
+    dgamma/dt = -(D^-1 A)^T gamma + dg/du(T - t), gamma(0) = 0 and returns it reversed in time,
+    lambda(t) = gamma(T - t), on the free rows."""
+    sysm = System(device).assemble(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
+                                   metaindex, logtransformconductivity)
+    try:
+        sysm.set_storage(float(Ss), np.asarray(volumes, np.float64))
+        nf = sysm.sizes()["nf_local"]
+        S = DeviceStepper(sysm, lambda t: np.asarray(getdgdu(tspan[1] - t), np.float64), adjoint=True, rtol=rtol,
+                          maxiter=maxiter)
+        gammas, tsg = _integrate(S, np.zeros(nf), dt0, tspan[0], tspan[1], stepper, atol, callback,
+                                 keep=lambda d: S.download(d))
+        if stats is not None:
+            stats.update(linear_solves=S.linear_solves, cg_iterations=S.cg_iterations, steps=len(tsg) - 1)
+        return gammas[::-1], [tspan[1] - t for t in tsg][::-1]
+    finally:
+        sysm.close()

@@ -1,0 +1,178 @@
+/*
+ * fvb200.h -- C ABI of libfvb200.so, the B200-native (sm_100a) replacement for the
+ * assemble -> solve hot path of madsjulia/FiniteVolume.jl.
+ *
+ * The reference has no FFI layer of its own: the boundary it exposes is its Julia call
+ * surface.  Every entry point below names the reference function (file:line, relative
+ * to the reference checkout) whose work it takes over; INTEGRATION.md shows the
+ * `ccall` shim (julia/FiniteVolumeB200.jl) that binds them under the reference's own
+ * function names.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  All index arrays on the wire are int64 and
+ *    1-based, exactly as Julia lays them out (`neighbors::Array{Pair{Int,Int},1}` is
+ *    2F interleaved int64: n1_1,n2_1,n1_2,n2_2,...).  Conversion to 0-based int32
+ *    happens on the device.
+ *  - Input pointers are borrowed for the duration of the call only and may be host
+ *    (pageable or pinned) or device pointers (cudaMemcpyDefault is used throughout).
+ *    Outputs are written into caller-allocated buffers (query sizes first).
+ *  - All device memory lives behind the opaque handle.  One handle = one GPU = one owner
+ *    thread at a time.  Multi-GPU = one process (or thread) per GPU, one handle each,
+ *    joined by fvb_comm_init().
+ *  - Every function returns an fvb_status; fvb_last_error() gives the thread-local
+ *    message.  Non-convergence of the solver is NOT an error (it mirrors
+ *    `ch.isconverged`, src/FiniteVolume.jl:161).
+ *  - There is no CPU fallback: without a CUDA device fvb_create() fails.
+ */
+#ifndef FVB200_H
+#define FVB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fvb_handle_s *fvb_handle;
+
+typedef enum {
+  FVB_OK = 0,
+  FVB_ERR_BAD_INPUT = 1,  /* what the reference reports with error()/BoundsError */
+  FVB_ERR_CUDA = 2,
+  FVB_ERR_NCCL = 3,
+  FVB_ERR_OOM = 4,
+  FVB_ERR_STATE = 5       /* call order violated (e.g. solve before assemble) */
+} fvb_status;
+
+#define FVB_UNIQUE_ID_BYTES 128
+
+/* ---- lifetime ------------------------------------------------------------------- */
+int fvb_version(void);
+const char *fvb_last_error(void);
+int fvb_device_count(int *count);
+/* Binds the handle to CUDA device `device` and creates its stream. */
+int fvb_create(int device, fvb_handle *out);
+int fvb_destroy(fvb_handle h);
+
+/* ---- multi-GPU (one rank per GPU; SURVEY 8e: slab partition by node index) -------- */
+/* Rank 0 calls fvb_comm_unique_id and ships the 128 bytes to the other ranks by any
+ * means (torch.distributed broadcast in the Python harness, MPI/Distributed in Julia);
+ * then every rank calls fvb_comm_init.  NCCL is dlopen'ed ("libnccl.so.2") on first use,
+ * so single-GPU users need no NCCL at all. */
+int fvb_comm_unique_id(uint8_t id[FVB_UNIQUE_ID_BYTES]);
+int fvb_comm_init(fvb_handle h, int nranks, int rank, const uint8_t id[FVB_UNIQUE_ID_BYTES]);
+
+/* ---- assembly: assembleA + assembleb (src/FiniteVolume.jl:75-108, :110-139) -------
+ * with getfreenodes (:32-44) and getnodei2dirichleti (:20-30) folded in.
+ *
+ *  n_nodes      N = length(sources) of the WHOLE problem
+ *  node_lo/hi   1-based inclusive range of nodes this rank owns (1, N for one GPU).
+ *               Rows (free nodes in ascending node order) are owned with their node.
+ *  n_faces      number of faces passed; they must be, in the global face order, ALL the
+ *               faces with at least one endpoint in [node_lo, node_hi]
+ *  neighbors    2*n_faces int64, interleaved pairs, global node ids
+ *  aol, cond    areasoverlengths[n_faces]; conductivities[n_cond]
+ *  metaindex    NULL for i -> i, else int64[n_faces], 1-based into cond (the table of the
+ *               reference's `metaindex` callable, src/FiniteVolume.jl:75)
+ *  logk         logtransformconductivity
+ *  sources      the owned slice sources[node_lo..node_hi]
+ *  dnodes/heads the FULL dirichletnodes / dirichletheads lists (every rank passes all)
+ *
+ * Produces, per owned row: the CSR row (columns ascending, duplicates left-folded in
+ * face order, explicit zeros kept -- the semantics of SparseArrays.sparse(I,J,V,m,n,+)
+ * at :107), b, and diag(A).  Fails with FVB_ERR_BAD_INPUT when a source sits on a
+ * Dirichlet node (the reference's error(), :25-27) or a node id is out of range. */
+int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo, int64_t node_hi,
+                 int64_t n_faces, const int64_t *neighbors, const double *aol,
+                 const double *cond, int64_t n_cond, const int64_t *metaindex, int logk,
+                 const double *sources, int64_t n_dirichlet, const int64_t *dnodes,
+                 const double *dheads);
+
+/* Values-only re-assembly on the retained structure (inverse loops re-solve on a fixed
+ * mesh: examples/box_model/ex.jl:53-64).  cond/metaindex/logk as in fvb_assemble;
+ * sources/dheads may be NULL to keep the previous ones. */
+int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk,
+                      const double *sources, const double *dheads);
+
+/* Sizes of this rank's part: free rows owned, stored entries, first owned row
+ * (1-based global free index), global free count, halo columns referenced. */
+int fvb_sizes(fvb_handle h, int64_t *nf_local, int64_t *nnz_local, int64_t *row_start,
+              int64_t *nf_global, int64_t *n_halo);
+
+/* The owned rows as the CSC/CSR arrays of a SparseMatrixCSC{Float64,Int64} (A is
+ * symmetric, so the same arrays serve as either): ptr[nf_local+1] 1-based into this
+ * rank's idx/val, idx = GLOBAL 1-based column (= Julia rowval), val = nzval. */
+int fvb_get_csr(fvb_handle h, int64_t *ptr, int64_t *idx, double *val);
+int fvb_get_b(fvb_handle h, double *b);                 /* assembleb, owned rows     */
+int fvb_get_diag(fvb_handle h, double *d);
+int fvb_get_freenode(fvb_handle h, uint8_t *freenode);  /* owned nodes; :32-44       */
+int fvb_get_nodei2freenodei(fvb_handle h, int64_t *map);/* owned nodes; -1 = Dirichlet */
+
+/* ---- halo plan (multi-GPU only) ---------------------------------------------------- */
+/* Global 1-based free indices of the off-rank columns this rank's rows reference,
+ * ascending; x[nf_local + k] on the device holds the value of halo column k. */
+int fvb_get_halo_cols(fvb_handle h, int64_t *cols);
+/* For every peer p (ascending rank): this rank receives recv_counts[p] consecutive halo
+ * entries from it (in halo order) and sends it the owned rows send_rows (0-based local
+ * row ids, concatenated per peer, send_counts[p] each). */
+int fvb_set_halo_plan(fvb_handle h, int n_peers, const int32_t *peer_ranks,
+                      const int64_t *send_counts, const int32_t *send_rows,
+                      const int64_t *recv_counts);
+
+/* ---- steady solve: the cg call of solvediffusion (src/FiniteVolume.jl:160-161) with
+ * Pl = Jacobi instead of Ruge-Stueben AMG (north_star), followed by freenodes2nodes
+ * (:141-155).  Stopping rule of IterativeSolvers.cg 0.8.1: ||r|| <= rtol * ||r0||.
+ *  x0_free      NULL (cg, x0 = 0) or the owned slice of an initial guess (cg!)
+ *  head_nodes   out, owned nodes [node_lo..node_hi]: solution on free nodes, prescribed
+ *               head on Dirichlet nodes; may be NULL
+ *  x_free       out, owned free rows; may be NULL
+ *  resnorm_hist out, first min(iters, hist_cap) residual norms (ch.data[:resnorm]) */
+int fvb_solve(fvb_handle h, double rtol, int64_t maxiter, const double *x0_free,
+              double *head_nodes, double *x_free, int64_t *iters, int *converged,
+              double *resnorm_hist, int64_t hist_cap);
+
+/* y = alpha * A x + beta * y on owned rows (host or device vectors of nf_local).
+ * Covers mul! inside cg, `b - A u` (src/transient.jl:197) and, A being symmetric, the
+ * adjoint's transpose product (:193).  Multi-GPU: collective (halo exchange inside). */
+int fvb_spmv(fvb_handle h, double alpha, const double *x, double beta, double *y);
+
+/* ---- transient: device-resident backward Euler (src/transient.jl:65-76, :188-205) --
+ * The handle keeps NSLOT work vectors of nf_local doubles so that the host-side step
+ * controller (src/transient.jl:78-154) moves no vectors over PCIe per step. */
+#define FVB_NSLOT 8
+int fvb_vec_upload(fvb_handle h, int slot, const double *host);
+int fvb_vec_download(fvb_handle h, int slot, double *host);
+int fvb_vec_copy(fvb_handle h, int dst, int src);
+int fvb_vec_load_b(fvb_handle h, int slot);              /* slot <- assembled b        */
+/* ||a - b||_2 over ALL ranks (LinearAlgebra.norm(onestep - twostep), :81). */
+int fvb_vec_diffnorm(fvb_handle h, int a, int b, double *out);
+/* D_r = Ss * volumes[node(r)] (scalebyvolume!, :7-22): pass the owned slice of volumes
+ * (node order, n_owned_nodes entries); NULL resets D to the identity. */
+int fvb_set_storage(fvb_handle h, double Ss, const double *volumes_owned_nodes);
+/* One backward-Euler solve, slot -> slot, in the SPD form of the reference's step:
+ *  adjoint = 0:  (A + D/dt) u+ = rhs_b + D u/dt            (== (D^-1 A + I/dt) u+ = D^-1 b + u/dt, :71-73)
+ *  adjoint = 1:  (A + D/dt) w  = rhs_b + u/dt, u+ = D w    (== (A D^-1 + I/dt) u+ = g + u/dt, :193,:203)
+ * rhs_slot holds the UNSCALED b (or the adjoint forcing g); warm start from u as the
+ * reference does (:73).  Returns FVB_ERR_BAD_INPUT for dt <= 0 (:68-70). */
+int fvb_step(fvb_handle h, int rhs_slot, int u_slot, double dt, int out_slot, int adjoint,
+             double rtol, int64_t maxiter, int64_t *iters, int *converged);
+/* Scatter a free-row slot to owned nodes (freenodes2nodes, src/transient.jl:172). */
+int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes);
+
+/* ---- measurement hooks (CUDA events on the handle's own stream) ------------------- */
+/* Average device time of one SpMV launch (K5) / one PCG iteration over `reps` launches
+ * on resident data, after `warmup` untimed ones. */
+int fvb_time_spmv(fvb_handle h, int warmup, int reps, double *ms_avg);
+/* Device times of the phases of the last fvb_assemble / fvb_solve on this handle. */
+typedef struct {
+  double h2d_ms, assemble_ms, solve_ms, d2h_ms;
+  double spmv_ms_total;    /* sum of SpMV kernel time inside the last solve, if profiled */
+  int64_t kernel_launches; /* kernels launched by the library since fvb_create */
+} fvb_timings;
+int fvb_get_timings(fvb_handle h, fvb_timings *out);
+int fvb_sync(fvb_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVB200_H */

@@ -1,0 +1,381 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+Bars (north_star): CSR structure bit-exact; assembled values bit-exact for plain K and within
+1e-14 relative for log K (device exp vs libm exp differ by <= 1 ulp); heads within 1e-8
+relative at matched tight residual tolerance."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RT_TIGHT = 1e-12
+
+
+def assert_csr_equal(A, Ao, exact_values=True):
+    assert A.shape == (Ao.m, Ao.n)
+    assert np.array_equal(A.colptr, Ao.colptr)
+    assert np.array_equal(A.rowval, Ao.rowval)
+    if exact_values:
+        assert np.array_equal(A.nzval, Ao.nzval)
+    else:
+        assert np.allclose(A.nzval, Ao.nzval, rtol=1e-14, atol=0.0)
+
+
+def box_problem(fv, ns, sigma=1.0, seed=0, mins=None, maxs=None):
+    """SURVEY 8d synthetic input: lognormal node K (seed 0), log-arithmetic-mean faces, left/right
+    Dirichlet 1/0 (examples/box_model/ex.jl:27-37)."""
+    mins = [0, 0, 0] if mins is None else mins
+    maxs = [n - 1 for n in ns] if maxs is None else maxs
+    _, nb, aol, vol = fv.regulargrid(mins, maxs, ns, want_coords=False)
+    N = int(np.prod(ns))
+    lnk = math.log(1e-5) + sigma * np.random.default_rng(seed).standard_normal(N)
+    kf = fv.nodehycos2neighborhycos(nb, lnk, True)
+    plane = ns[1] * ns[2]
+    dn = np.concatenate([np.arange(1, plane + 1), np.arange(N - plane + 1, N + 1)])
+    dh = np.concatenate([np.ones(plane), np.zeros(plane)])
+    return nb, aol, kf, np.zeros(N), dn, dh, vol
+
+
+def test_runtests_chain(fv):
+    """test/runtests.jl:4-16."""
+    nb = [(1, 2), (2, 1), (2, 3), (3, 2), (3, 4), (4, 3)]
+    h, ch, A, b, fn = fv.solvediffusion(nb, np.ones(6), np.ones(6), np.zeros(4), [1, 4], [1.0, 0.0])
+    assert np.allclose(h, [1.0, 2 / 3, 1 / 3, 0.0], rtol=math.sqrt(np.finfo(float).eps))
+    assert np.array_equal(A.toscipy().toarray(), [[4.0, -2.0], [-2.0, 4.0]])
+    assert np.array_equal(b, [2.0, 0.0])
+    assert list(fn) == [False, True, True, False]
+    assert ch.isconverged and ch.iters == len(ch.data["resnorm"]) <= 2
+
+
+@pytest.mark.parametrize("logk", [False, True])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_multigraph(fv, orc, logk, seed):
+    """Duplicate faces, both directions, self loops, duplicate Dirichlet entries (last wins),
+    a metaindex table, sources -- everything sparse(...,+) has to fold."""
+    rng = np.random.default_rng(seed)
+    N, F, ND = 400, 2500, 40
+    nb = rng.integers(1, N + 1, size=(F, 2))
+    nb[::50, 1] = nb[::50, 0]  # guaranteed self loops
+    aol = rng.random(F) + 0.05
+    ncond = 37
+    cond = rng.standard_normal(ncond) if logk else rng.random(ncond) + 0.1
+    meta = rng.integers(1, ncond + 1, size=F)
+    dn = rng.choice(np.arange(1, N + 1), ND, replace=False)
+    dn = np.concatenate([dn, dn[:5]])  # duplicates: the later head wins
+    dh = rng.random(dn.size)
+    src = rng.standard_normal(N)
+    src[dn - 1] = 0
+    A = fv.assembleA(nb, aol, cond, src, dn, dh, meta, logk)
+    Ao = orc.assembleA(nb, aol, cond, src, dn, dh, meta, logk)
+    assert_csr_equal(A, Ao, exact_values=not logk)
+    b = fv.assembleb(nb, aol, cond, src, dn, dh, lambda i: int(meta[i - 1]), logk)
+    bo = orc.assembleb(nb, aol, cond, src, dn, dh, meta, logk)
+    if logk:
+        assert np.allclose(b, bo, rtol=1e-13, atol=1e-14)
+    else:
+        assert np.array_equal(b, bo)
+    fn, n2f = fv.getfreenodes(N, dn)
+    fno, n2fo = orc.getfreenodes(N, dn)
+    assert np.array_equal(fn, fno) and np.array_equal(n2f, n2fo)
+
+
+def test_high_degree_rows(fv, orc):
+    """A hub with 150 incident faces (with repeats) takes the long-row path of the row kernels."""
+    rng = np.random.default_rng(3)
+    N = 120
+    hub = 7
+    others = rng.integers(1, N + 1, size=150)
+    nb = np.stack([np.where(rng.random(150) < 0.5, hub, others), np.zeros(150, int)], axis=1)
+    nb[:, 1] = np.where(nb[:, 0] == hub, others, hub)
+    ring = np.stack([np.arange(1, N), np.arange(2, N + 1)], axis=1)
+    nb = np.concatenate([nb, ring, nb[:20, ::-1]])
+    rng.shuffle(nb)
+    F = nb.shape[0]
+    aol, k = rng.random(F) + 0.1, rng.random(F) + 0.1
+    dn, dh = np.array([1, 60, N]), np.array([3.0, 1.0, 2.0])
+    src = np.zeros(N)
+    A = fv.assembleA(nb, aol, k, src, dn, dh)
+    Ao = orc.assembleA(nb, aol, k, src, dn, dh)
+    assert_csr_equal(A, Ao)
+    assert np.array_equal(fv.assembleb(nb, aol, k, src, dn, dh), orc.assembleb(nb, aol, k, src, dn, dh))
+
+
+def test_edge_cases(fv, orc):
+    # no faces at all: empty rows, b = sources on free nodes
+    s = fv.System().assemble(np.empty((0, 2), np.int64), [], [], [1.0, 2.0, 0.0], [3], [5.0])
+    assert s.sizes()["nf_local"] == 2 and s.sizes()["nnz_local"] == 0
+    assert np.array_equal(s.b(), [1.0, 2.0])
+    p, i, v = s.csr()
+    assert list(p) == [1, 1, 1] and i.size == 0
+    # every node Dirichlet: a 0x0 system, heads are the prescribed ones
+    h, ch, A, b, fn = fv.solvediffusion([(1, 2)], [1.0], [1.0], [0.0, 0.0], [1, 2], [4.0, 5.0])
+    assert list(h) == [4.0, 5.0] and A.shape == (0, 0) and b.size == 0 and ch.iters == 0
+    # no Dirichlet nodes: assembles (singular) like the reference does
+    nb = [(1, 2), (2, 3)]
+    A = fv.assembleA(nb, [1.0, 2.0], [1.0, 1.0], np.zeros(3), [], [])
+    assert_csr_equal(A, orc.assembleA(nb, [1.0, 2.0], [1.0, 1.0], np.zeros(3), [], []))
+    # isolated free node -> empty row in the middle; face between two Dirichlet nodes -> nothing
+    nb = [(1, 2), (4, 5), (5, 1)]
+    args = (nb, [1.0, 2.0, 3.0], [1.0, 1.0, 1.0], np.zeros(5), [4, 5], [1.0, 2.0])
+    assert_csr_equal(fv.assembleA(*args), orc.assembleA(*args))
+    assert np.array_equal(fv.assembleb(*args), orc.assembleb(*args))
+
+
+def test_errors(fv):
+    """The reference's error() cases surface as FVB_ERR_BAD_INPUT with the reference's message."""
+    with pytest.raises(fv.FVBError, match="There cannot be a source at a Dirichlet node, but node 2") as e:
+        fv.assembleb([(1, 2)], [1.0], [1.0], [0.0, 1.0], [2], [0.0])
+    assert e.value.status == 1
+    with pytest.raises(fv.FVBError, match="out of range"):
+        fv.assembleA([(1, 9)], [1.0], [1.0], [0.0, 0.0], [2], [0.0])
+    with pytest.raises(fv.FVBError, match="out of range"):
+        fv.assembleA([(1, 2)], [1.0], [1.0], [0.0, 0.0], [0], [0.0])
+    with pytest.raises(fv.FVBError, match="metaindex"):
+        fv.assembleA([(1, 2)], [1.0], [1.0], [0.0, 0.0], [2], [0.0], [3])
+    s = fv.System()
+    with pytest.raises(fv.FVBError) as e:
+        s.solve()
+    assert e.value.status == 5
+
+
+def test_fourfractures(fv, orc, fourfractures):
+    """BASELINE config 3: the irregular discrete-fracture graph shipped with the reference."""
+    m = fourfractures
+    src = np.zeros(m["xs"].size)
+    args = (m["neighbors"], m["areasoverlengths"], m["conductivities"], src, m["dirichletnodes"], m["dirichletheads"])
+    h, ch, A, b, fn = fv.solvediffusion(*args, rtol=RT_TIGHT)
+    ho, cho, Ao, bo, fno = orc.solvediffusion(*args, maxiter=20000, tol=RT_TIGHT)
+    assert A.shape == (2076, 2076) and A.nzval.size == 14528
+    assert_csr_equal(A, Ao)
+    assert np.array_equal(b, bo) and np.array_equal(fn, fno)
+    assert ch.isconverged and abs(ch.iters - cho.iters) <= 3
+    assert np.max(np.abs(h - ho)) <= 1e-8 * np.max(np.abs(ho))
+    assert np.max(np.abs(h - m["pflotran_h"])) / 2e6 < 1.5e-2
+    # the reference's default tolerance: same iteration count class as the oracle (SURVEY: 172)
+    h2, ch2, *_ = fv.solvediffusion(*args)
+    _, cho2, *_ = orc.solvediffusion(*args, maxiter=20000)
+    assert ch2.isconverged and abs(ch2.iters - cho2.iters) <= 2
+    assert np.allclose(ch2.data["resnorm"][:50], cho2.data["resnorm"][:50], rtol=1e-6)
+
+
+@pytest.mark.parametrize("sigma", [0.0, 1.0])
+def test_config1_grid_100x100x2(fv, orc, sigma):
+    """BASELINE config 1: regulargrid([-50,-50,0],[50,50,10],[100,100,2]), k=1e-5 / lognormal."""
+    ns = [100, 100, 2]
+    nb, aol, lnkf, src, dn, dh, _ = box_problem(fv, ns, sigma, mins=[-50, -50, 0], maxs=[50, 50, 10])
+    k = np.exp(lnkf)
+    h, ch, A, b, fn = fv.solvediffusion(nb, aol, k, src, dn, dh, rtol=RT_TIGHT)
+    ho, cho, Ao, bo, _ = orc.solvediffusion(nb, aol, k, src, dn, dh, maxiter=50000, tol=RT_TIGHT)
+    assert A.shape == (19600, 19600) and A.nzval.size == 116808
+    assert_csr_equal(A, Ao)
+    assert np.array_equal(b, bo)
+    assert ch.isconverged and np.max(np.abs(h - ho)) <= 1e-8
+    assert h.min() >= -1e-9 and h.max() <= 1 + 1e-9  # examples/box_model/ex_piml_data.jl:49-51
+
+
+def test_grid_64cubed_lognormal_logk(fv, orc):
+    nb, aol, lnkf, src, dn, dh, _ = box_problem(fv, [64, 64, 64], 1.0)
+    h, ch, A, b, fn = fv.solvediffusion(nb, aol, lnkf, src, dn, dh, rtol=RT_TIGHT, logtransformconductivity=True)
+    ho, cho, Ao, bo, _ = orc.solvediffusion(nb, aol, lnkf, src, dn, dh, maxiter=50000, tol=RT_TIGHT,
+                                            logtransformconductivity=True, threaded=True)
+    assert_csr_equal(A, Ao, exact_values=False)
+    assert np.allclose(b, bo, rtol=1e-14, atol=0)
+    assert ch.isconverged and cho.isconverged
+    assert np.max(np.abs(h - ho)) <= 1e-8 * np.max(np.abs(ho))
+
+
+def test_cg_semantics(fv, orc):
+    """IterativeSolvers.cg stopping rule and history; cg! warm start (src/transient.jl:51-52)."""
+    nb, aol, lnkf, src, dn, dh, _ = box_problem(fv, [20, 16, 12], 1.0)
+    k = np.exp(lnkf)
+    s = fv.System().assemble(nb, aol, k, src, dn, dh)
+    Ao = orc.assembleA(nb, aol, k, src, dn, dh)
+    bo = orc.assembleb(nb, aol, k, src, dn, dh)
+    _, x, ch = s.solve(want_x=True)
+    xo, cho = orc.cg(Ao, bo, maxiter=10000)
+    assert ch.isconverged and abs(ch.iters - cho.iters) <= 1
+    n = min(ch.iters, cho.iters) - 1
+    assert np.allclose(ch.data["resnorm"][:n], cho.data["resnorm"][:n], rtol=1e-5)
+    assert ch.data["resnorm"][-1] <= fv.SQRT_EPS * np.linalg.norm(bo)
+    # maxiter reached: not an error, reported through the history (ch.isconverged false)
+    _, _, ch5 = s.solve(maxiter=5)
+    assert not ch5.isconverged and ch5.iters == 5 and len(ch5.data["resnorm"]) == 5
+    # warm start: tolerance is relative to the residual of x0
+    x0 = x * (1 + 1e-3 * np.sin(np.arange(x.size)))
+    _, x2, chw = s.solve(x0=x0, want_x=True)
+    x2o, chwo = orc.cg(Ao, bo, x0=x0, maxiter=10000)
+    assert chw.isconverged and abs(chw.iters - chwo.iters) <= 1 and chw.iters < ch.iters
+    assert np.allclose(x2, x2o, rtol=1e-6, atol=1e-9)
+    # already converged start: zero iterations
+    _, _, ch0 = s.solve(x0=np.zeros_like(x), maxiter=0)
+    assert ch0.iters == 0
+
+
+def test_spmv_and_residual(fv, orc):
+    """mul! inside cg and `A*head[freenode]-b` (examples/waffle/ex.jl:16)."""
+    nb, aol, lnkf, src, dn, dh, _ = box_problem(fv, [17, 9, 11], 2.0)
+    k = np.exp(lnkf)
+    h, ch, A, b, fn = fv.solvediffusion(nb, aol, k, src, dn, dh, rtol=RT_TIGHT)
+    Ao = orc.assembleA(nb, aol, k, src, dn, dh)
+    x = np.random.default_rng(5).standard_normal(A.n)
+    y = A @ x
+    assert np.allclose(y, orc.spmv(Ao, x), rtol=1e-13, atol=1e-18)
+    res = A @ h[fn] - b
+    assert np.linalg.norm(res) <= 10 * RT_TIGHT * np.linalg.norm(b)
+    # y = alpha A x + beta y
+    y0 = np.arange(A.n, dtype=float)
+    assert np.allclose(A._sys.spmv(x, alpha=-1.0, beta=2.0, y=y0), -orc.spmv(Ao, x) + 2 * y0, rtol=1e-13, atol=1e-18)
+
+
+def test_update_values_and_determinism(fv, orc):
+    nb, aol, lnkf, src, dn, dh, _ = box_problem(fv, [24, 20, 16], 1.0)
+    s = fv.System().assemble(nb, aol, lnkf, src, dn, dh, None, True)
+    p1, i1, v1 = s.csr()
+    s2 = fv.System().assemble(nb, aol, lnkf, src, dn, dh, None, True)
+    p2, i2, v2 = s2.csr()
+    assert np.array_equal(p1, p2) and np.array_equal(i1, i2) and np.array_equal(v1, v2)  # run-to-run bitwise
+    assert np.array_equal(s.b(), s2.b())
+    lnk2 = lnkf + 0.3 * np.cos(np.arange(lnkf.size))
+    dh2 = dh * 2 + 1
+    s.update_values(lnk2, dirichletheads=dh2)
+    s3 = fv.System().assemble(nb, aol, lnk2, src, dn, dh2, None, True)
+    p3, i3, v3 = s3.csr()
+    pu, iu, vu = s.csr()
+    assert np.array_equal(pu, p3) and np.array_equal(iu, i3) and np.array_equal(vu, v3)
+    assert np.array_equal(s.b(), s3.b()) and np.array_equal(s.diag(), s3.diag())
+    Ao = orc.assembleA(nb, aol, lnk2, src, dn, dh2, None, True)
+    assert np.allclose(vu, Ao.nzval, rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_slab_partition_emulated(fv, orc, nranks):
+    """SURVEY 8e on one GPU: every 'rank' assembles only its slab; stacked rows must equal the
+    unpartitioned CSR bit for bit, and the halo plans must be mutually consistent."""
+    import importlib
+    dist = importlib.import_module("fvb200.distributed")
+    ns = [9, 6, 5]
+    nb, aol, lnkf, src, dn, dh, _ = box_problem(fv, ns, 1.0)
+    src = np.random.default_rng(2).standard_normal(src.size)
+    src[dn - 1] = 0
+    k = np.exp(lnkf)
+    Ao = orc.assembleA(nb, aol, k, src, dn, dh)
+    bo = orc.assembleb(nb, aol, k, src, dn, dh)
+    N = src.size
+    planes = dist.slab_planes(ns[0], nranks)
+    systems, ranges, halos = [], [], []
+    for r in range(nranks):
+        lo, hi = dist.node_range_of_planes(planes[r], ns[1], ns[2])
+        touch = ((nb[:, 0] >= lo) & (nb[:, 0] <= hi)) | ((nb[:, 1] >= lo) & (nb[:, 1] <= hi))
+        s = fv.System().assemble(nb[touch], aol[touch], k[touch], src[lo - 1:hi], dn, dh, n_nodes=N, node_range=(lo, hi))
+        systems.append(s)
+        sz = s.sizes()
+        assert sz["nf_global"] == Ao.n
+        ranges.append((sz["row_start"], sz["nf_local"]))
+        halos.append(s.halo_cols())
+    assert ranges[0][0] == 1 and sum(r[1] for r in ranges) == Ao.n
+    ptr, idx, val, b = [np.array([1])], [], [], []
+    for s in systems:
+        p, i, v = s.csr()
+        ptr.append(p[1:] - 1 + ptr[-1][-1])
+        idx.append(i); val.append(v); b.append(s.b())
+    assert np.array_equal(np.concatenate(ptr), Ao.colptr)
+    assert np.array_equal(np.concatenate(idx), Ao.rowval)
+    assert np.array_equal(np.concatenate(val), Ao.nzval)
+    assert np.array_equal(np.concatenate(b), bo)
+    # slab neighbours exchange exactly one plane of free rows
+    plans = [dist.halo_plan_from_ranges(r, ranges, halos) for r in range(nranks)]
+    for r, (peers, sc, sr, rc) in enumerate(plans):
+        assert peers == [p for p in (r - 1, r + 1) if 0 <= p < nranks]
+        for p, c in zip(peers, rc):
+            q = plans[p]
+            assert q[1][q[0].index(r)] == c  # what r receives from p is what p sends to r
+        assert sum(rc) == halos[r].size == len(peers) * ns[1] * ns[2]
+    # same test with the full face list handed to every rank (supersets are allowed)
+    lo, hi = dist.node_range_of_planes(planes[-1], ns[1], ns[2])
+    s = fv.System().assemble(nb, aol, k, src[lo - 1:hi], dn, dh, n_nodes=N, node_range=(lo, hi))
+    assert np.array_equal(s.csr()[2], systems[-1].csr()[2])
+
+
+def test_onenode_transient_and_adjoint(fv):
+    """test/onenodeadjoint.jl:29-44,56-64."""
+    p = dict(Ss=1.0, volumes=[1.0, 1.0], neighbors=[(1, 2)], aol=[1.0], loghycos=np.array([0.0]),
+             sources=[0.0, 1.0], dn=[1], dh=[0.0], u0=[0.0, 0.0], tspan=(0.0, 1.0), atol=1e-8, dt0=1e-3)
+    us, ts = fv.backwardeulerintegrate(p["u0"], p["tspan"], p["Ss"], p["volumes"], p["neighbors"], p["aol"],
+                                       p["loghycos"], p["sources"], p["dn"], p["dh"], None, True, atol=p["atol"],
+                                       dt0=p["dt0"], rtol=1e-12)
+    assert ts[-1] == 1.0
+    for u, t in zip(us[1:], ts[1:]):
+        assert math.isclose(u[1], 1 - math.exp(-t), rel_tol=1e-4) and u[0] == 0.0
+    sigma2 = 0.01**2
+    f = lambda s: 2 * sigma2 * ((1 - math.exp(-math.e * s)) / math.e - (1 - math.exp(-s)))  # noqa: E731
+    lam, tl = fv.adjointintegrate(lambda t: np.array([f(t)]), p["tspan"], p["Ss"], p["volumes"], p["neighbors"],
+                                  p["aol"], p["loghycos"] + 1, p["sources"], p["dn"], p["dh"], None, True,
+                                  atol=p["atol"], dt0=p["dt0"], rtol=1e-12)
+    from scipy.integrate import quad
+    for lv, t in zip(lam, tl):
+        s_ = 1.0 - t
+        gamma = math.exp(-math.e * s_) * quad(lambda s: math.exp(math.e * s) * f(1.0 - s), 0, s_)[0]
+        assert math.isclose(lv[0], gamma, rel_tol=1e-4, abs_tol=1e-7)
+
+
+def test_transient_step_matches_oracle(fv, orc):
+    """One forward and one adjoint backward-Euler solve (src/transient.jl:65-76, :193) on a small
+    heterogeneous box with non-uniform volumes, against a direct solve of the reference's scaled
+    (D^-1 A + I/dt) system."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    ns = [7, 6, 5]
+    nb, aol, lnkf, src, dn, dh, vol = box_problem(fv, ns, 1.0)
+    k = np.exp(lnkf)
+    src = 1e-6 * np.random.default_rng(4).standard_normal(src.size)
+    src[dn - 1] = 0
+    Ss, dt = 0.1, 37.0
+    s = fv.System().assemble(nb, aol, k, src, dn, dh)
+    s.set_storage(Ss, vol)
+    fn = s.freenode()
+    D = Ss * vol[fn]
+    A = orc.assembleA(nb, aol, k, src, dn, dh).toscipy().tocsr()
+    b = orc.assembleb(nb, aol, k, src, dn, dh)
+    At = sp.diags(1 / D) @ A
+    u = np.random.default_rng(6).random(D.size)
+    M = (At + sp.identity(D.size) / dt).tocsc()
+    ref = spla.spsolve(M, b / D + u / dt)
+    s.vec_load_b(0)
+    s.vec_upload(1, u)
+    it, conv = s.step(0, 1, dt, 2, rtol=1e-13)
+    assert conv and np.allclose(s.vec_download(2), ref, rtol=1e-9, atol=1e-12)
+    g = np.random.default_rng(8).random(D.size)
+    refa = spla.spsolve((At.T + sp.identity(D.size) / dt).tocsc(), g + u / dt)
+    s.vec_upload(0, g)
+    it, conv = s.step(0, 1, dt, 3, adjoint=True, rtol=1e-13)
+    assert conv and np.allclose(s.vec_download(3), refa, rtol=1e-9, atol=1e-12)
+    assert math.isclose(s.vec_diffnorm(2, 3), np.linalg.norm(s.vec_download(2) - s.vec_download(3)), rel_tol=1e-12)
+    with pytest.raises(fv.FVBError, match="time step must be positive"):
+        s.step(0, 1, 0.0, 2)
+
+
+def test_theis_transient(fv, orc):
+    """BASELINE config 4 / test/theis.jl:52-65: Thiem (steady) and Theis (10 days, dt0=60,
+    atol=1e-4) within isapprox(atol=1e-4, rtol=2e-2); the controller must walk the same
+    1090-step / 3283-solve trajectory as the reference restatement."""
+    from test_oracle_pins import theis_expected, theis_setup
+    P = theis_setup(fv)
+    assert P["dn"].size == 4752
+    tend = 60 * 60 * 24 * 1e1
+    theis, thiem = theis_expected(P, tend)
+    usteady, ch, A, b, fn = fv.solvediffusion(P["nb"], P["aol"], P["hycos"], P["src"], P["dn"], P["dh"], rtol=RT_TIGHT)
+    assert A.shape == (15650, 15650) and A.nzval.size == 93108 and ch.isconverged
+    dd = P["steadyhead"] - usteady[P["good"]]
+    assert np.linalg.norm(thiem - dd) <= max(1e-4, 2e-2 * max(np.linalg.norm(thiem), np.linalg.norm(dd)))
+    u0 = np.full(P["src"].size, P["steadyhead"])
+    stats = {}
+    us, ts = fv.backwardeulerintegrate(u0, (0.0, tend), P["Ss"], P["vol"], P["nb"], P["aol"], P["hycos"], P["src"],
+                                       P["dn"], P["dh"], atol=1e-4, dt0=60.0, rtol=1e-10, stats=stats)
+    assert ts[-1] == tend and stats["steps"] == 1090 and stats["linear_solves"] == 3283
+    dd = P["steadyhead"] - us[-1][P["good"]]
+    assert np.linalg.norm(theis - dd) <= max(1e-4, 2e-2 * max(np.linalg.norm(theis), np.linalg.norm(dd)))
+    uso, tso = orc.backwardeulerintegrate(u0, (0.0, tend), P["Ss"], P["vol"], P["nb"], P["aol"], P["hycos"], P["src"],
+                                          P["dn"], P["dh"], atol=1e-4, dt0=60.0)
+    assert np.allclose(ts, tso, rtol=0, atol=0)
+    assert np.max(np.abs(us[-1] - uso[-1])) <= 1e-6

@@ -1,0 +1,161 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/fvb200.h declares,
+refuses to run without a GPU (no CPU fallback), and the host-side helpers (grid builder, step
+controller, slab planning) agree with the oracle / the reference's own tests."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(fv):
+    hdr = open(os.path.join(ROOT, "include", "fvb200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|const char \*)\s*(fvb_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
+    assert len(declared) >= 30
+    assert declared == set(fv._lib.SYMBOLS)
+    L = ctypes.CDLL(fv.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.fvb_version() >= 100
+
+
+def test_no_cpu_fallback(fv):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(fv.FVBError, match="no CPU fallback") as e:
+        fv.System(0)
+    assert e.value.status == 2
+    with pytest.raises(fv.FVBError):
+        fv.solvediffusion([(1, 2)], [1.0], [1.0], [0.0, 0.0], [1], [0.0])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "finitevolume.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "fv_oracle" not in txt and "oracle/" not in txt, f
+
+
+@pytest.mark.parametrize("mins,maxs,ns", [([0, 0, 0], [3, 2, 1], [4, 3, 2]),
+                                          ([-50, -50, 0], [50, 50, 10], [20, 10, 2]),
+                                          ([0, 0, 0], [6, 5, 4], [7, 6, 5])])
+def test_regulargrid_matches_oracle(fv, orc, mins, maxs, ns):
+    """src/grid.jl:56-110: identical ordering and values as the serial triple loop."""
+    c, nb, aol, vol = fv.regulargrid(mins, maxs, ns)
+    co, nbo, aolo, volo = orc.regulargrid(mins, maxs, ns)
+    assert np.array_equal(nb, nbo) and np.array_equal(aol, aolo) and np.array_equal(vol, volo)
+    assert np.allclose(c, co, rtol=0, atol=1e-12)
+    assert fv.grid_sizes(ns) == (int(np.prod(ns)), nb.shape[0])
+
+
+def test_regulargrid_rejects_non_3d(fv):
+    with pytest.raises(ValueError, match="only 3 dimensions supported"):  # src/grid.jl:59
+        fv.regulargrid([0, 0], [1, 1], [2, 2])
+
+
+def test_regulargrid_slabs_cover_global_list(fv):
+    """Each rank's slab list = the faces touching its planes, in global order."""
+    import importlib
+    dist = importlib.import_module("fvb200.distributed")
+    ns = [9, 4, 3]
+    _, nb, aol, vol = fv.regulargrid([0, 0, 0], [8, 3, 2], ns)
+    for nranks in (1, 2, 4):
+        planes = dist.slab_planes(ns[0], nranks)
+        assert planes[0][0] == 1 and planes[-1][1] == ns[0]
+        vols = []
+        for pl in planes:
+            lo, hi = dist.node_range_of_planes(pl, ns[1], ns[2])
+            _, nbs, aols, vs = fv.regulargrid([0, 0, 0], [8, 3, 2], ns, planes=pl)
+            touch = ((nb[:, 0] >= lo) & (nb[:, 0] <= hi)) | ((nb[:, 1] >= lo) & (nb[:, 1] <= hi))
+            assert np.array_equal(nbs, nb[touch]) and np.array_equal(aols, aol[touch])
+            vols.append(vs)
+        assert np.array_equal(np.concatenate(vols), vol)
+
+
+def test_slab_planes_balance_free_planes(fv):
+    import importlib
+    dist = importlib.import_module("fvb200.distributed")
+    pl = dist.slab_planes(512, 8)
+    free = [hi - lo + 1 - (1 if r in (0, 7) else 0) for r, (lo, hi) in enumerate(pl)]
+    assert max(free) - min(free) <= 1 and sum(hi - lo + 1 for lo, hi in pl) == 512
+    assert dist.slab_planes(4, 4) == [(1, 1), (2, 2), (3, 3), (4, 4)]
+    with pytest.raises(ValueError):
+        dist.slab_planes(3, 4)
+
+
+def test_nodehycos2neighborhycos(fv, orc):
+    """src/grid.jl:14-33: geometric mean / arithmetic mean of logs, (n3,n2,n1) layout."""
+    ns = [4, 3, 5]
+    _, nb, _, _ = fv.regulargrid([0, 0, 0], [3, 2, 4], ns)
+    k = np.random.default_rng(0).random((ns[2], ns[1], ns[0])) + 0.1
+    for lg in (False, True):
+        assert np.array_equal(fv.nodehycos2neighborhycos(nb, k, lg), orc.nodehycos2neighborhycos(nb, k, lg))
+    f1 = fv.nodehycos2neighborhycos(nb, k)[0]
+    assert math.isclose(f1, math.sqrt(k[0, 0, 0] * k[0, 0, 1]))  # face 1 = node 1 => node 1+n2*n3
+
+
+def test_ode_controller_with_linearsolver_hook(fv):
+    """test/ode.jl:8-40 -- the generic integrator with a caller-supplied linear solver."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    v = np.array([1.0, 2.0, 3.0])
+    ys, ts = fv.backwardeulerintegrate_generic(np.ones(3), sp.diags(v).tocsr(), np.zeros(3), 1e-4, 0.0, 0.25, atol=1e-8,
+                                               linearsolver=lambda A, b, x0: spla.spsolve(A.tocsc(), b))
+    assert ts[-1] == 0.25
+    for y, t in zip(ys, ts):
+        assert np.allclose(y, np.exp(-v * t), atol=1e-4)
+    A = -np.array([[0.5, -1.0], [1.0, -1.0]])
+
+    def exact(t, c1=1, c2=2):
+        s7 = math.sqrt(7)
+        a, b_ = np.array([1, 0.75]), np.array([0, -s7 / 4])
+        return (c1 * math.exp(-t / 4) * (a * math.cos(s7 * t / 4) - b_ * math.sin(s7 * t / 4))
+                + c2 * math.exp(-t / 4) * (a * math.sin(s7 * t / 4) + b_ * math.cos(s7 * t / 4)))
+    ys, ts = fv.backwardeulerintegrate_generic(exact(0), A, np.zeros(2), 1e-4, 0.0, 0.5, atol=1e-8,
+                                               linearsolver=lambda M, b, x0: np.linalg.solve(M, b))
+    for y, t in zip(ys, ts):
+        assert np.allclose(y, exact(t), atol=1e-4)
+    with pytest.raises(RuntimeError, match="no CPU solver"):
+        fv.backwardeulerintegrate_generic(np.ones(3), sp.diags(v).tocsr(), np.zeros(3), 1e-4, 0.0, 2.0)
+
+
+def test_controller_matches_oracle_trajectory(fv, orc):
+    """The step-doubling controller (src/transient.jl:78-154) restated twice -- product host code
+    vs oracle -- must take the same accepted steps when both use exact solves."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    rng = np.random.default_rng(1)
+    n = 12
+    M = sp.random(n, n, 0.3, random_state=2)
+    A = (M @ M.T + sp.diags(rng.random(n) + 0.5)).tocsr()
+    b = rng.random(n)
+    u0 = rng.random(n)
+    ys, ts = fv.backwardeulerintegrate_generic(u0, A, b, 0.5, 0.0, 7.0, atol=1e-3,
+                                               linearsolver=lambda S, r, x0: spla.spsolve(S.tocsc(), r))
+    uso, tso = orc.backwardeulerintegrate_core(u0, A, b, 0.5, 0.0, 7.0, atol=1e-3,
+                                               linearsolver=lambda A_, dt, r, x0: spla.spsolve(
+                                                   (A_ + sp.identity(n) / dt).tocsc(), r))
+    assert ts == tso
+    assert np.allclose(np.array(ys), np.array(uso), rtol=1e-10)
+
+
+def test_halo_plan_pure(fv):
+    import importlib
+    dist = importlib.import_module("fvb200.distributed")
+    ranges = [(1, 10), (11, 10), (21, 5)]
+    halos = [np.array([11, 12]), np.array([9, 10, 21]), np.array([20])]
+    p0 = dist.halo_plan_from_ranges(0, ranges, halos)
+    p1 = dist.halo_plan_from_ranges(1, ranges, halos)
+    p2 = dist.halo_plan_from_ranges(2, ranges, halos)
+    assert p0[0] == [1] and p0[1] == [2] and list(p0[2]) == [8, 9] and p0[3] == [2]
+    assert p1[0] == [0, 2] and p1[1] == [2, 1] and list(p1[2]) == [0, 1, 9] and p1[3] == [2, 1]
+    assert p2[0] == [1] and p2[1] == [1] and list(p2[2]) == [0] and p2[3] == [1]
+    with pytest.raises(ValueError):
+        dist.halo_plan_from_ranges(0, ranges, [np.array([5]), halos[1], halos[2]])
