@@ -19,13 +19,14 @@ SYMBOLS = [
     "fvb_get_csr", "fvb_get_b", "fvb_get_diag", "fvb_get_freenode", "fvb_get_nodei2freenodei",
     "fvb_get_halo_cols", "fvb_set_halo_plan", "fvb_solve", "fvb_spmv", "fvb_vec_upload",
     "fvb_vec_download", "fvb_vec_copy", "fvb_vec_load_b", "fvb_vec_diffnorm", "fvb_set_storage",
-    "fvb_step", "fvb_vec_to_nodes", "fvb_time_spmv", "fvb_get_timings", "fvb_sync",
+    "fvb_step", "fvb_vec_to_nodes", "fvb_time_spmv", "fvb_set_profiling", "fvb_get_timings", "fvb_sync",
 ]
 
 
 class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("assemble_ms", C.c_double), ("solve_ms", C.c_double),
-                ("d2h_ms", C.c_double), ("spmv_ms_total", C.c_double), ("kernel_launches", C.c_int64)]
+                ("d2h_ms", C.c_double), ("spmv_ms_total", C.c_double), ("spmv_samples", C.c_int64),
+                ("kernel_launches", C.c_int64)]
 
 
 class FVBError(RuntimeError):

@@ -114,6 +114,28 @@ class System:
         self._logk = bool(logtransformconductivity)
         return self
 
+    def assemble_raw(self, n_nodes, node_lo, node_hi, n_faces, neighbors_ptr, aol_ptr, cond_ptr, n_cond, meta_ptr,
+                     logk, sources_ptr, n_dirichlet, dnodes_ptr, dheads_ptr):
+        """fvb_assemble on raw addresses (host, pinned or device -- e.g. torch tensors' data_ptr());
+        nothing is copied or converted on the Python side."""
+        vp = lambda a: C.c_void_p(a) if a else None  # noqa: E731
+        check(lib().fvb_assemble(self._h, C.c_int64(n_nodes), C.c_int64(node_lo), C.c_int64(node_hi),
+                                 C.c_int64(n_faces), vp(neighbors_ptr), vp(aol_ptr), vp(cond_ptr), C.c_int64(n_cond),
+                                 vp(meta_ptr), C.c_int(int(bool(logk))), vp(sources_ptr), C.c_int64(n_dirichlet),
+                                 vp(dnodes_ptr), vp(dheads_ptr)))
+        self.node_lo, self.node_hi = int(node_lo), int(node_hi)
+        self._logk = bool(logk)
+        return self
+
+    def solve_raw(self, rtol, maxiter, head_ptr=0, x_ptr=0, x0_ptr=0):
+        """fvb_solve on raw addresses; returns (iters, converged)."""
+        vp = lambda a: C.c_void_p(a) if a else None  # noqa: E731
+        iters = C.c_int64()
+        conv = C.c_int()
+        check(lib().fvb_solve(self._h, C.c_double(rtol), C.c_int64(int(maxiter)), vp(x0_ptr), vp(head_ptr), vp(x_ptr),
+                              C.byref(iters), C.byref(conv), None, C.c_int64(0)))
+        return int(iters.value), bool(conv.value)
+
     def update_values(self, conductivities, sources=None, dirichletheads=None, logtransformconductivity=None):
         cond = f64(conductivities)
         logk = self._logk if logtransformconductivity is None else bool(logtransformconductivity)
@@ -238,6 +260,9 @@ class System:
         out = C.c_double()
         check(lib().fvb_time_spmv(self._h, C.c_int(warmup), C.c_int(reps), C.byref(out)))
         return out.value
+
+    def set_profiling(self, stride):
+        check(lib().fvb_set_profiling(self._h, C.c_int(int(stride))))
 
     def timings(self):
         t = _lib.Timings()

@@ -101,5 +101,11 @@ struct fvb_handle_s {
   int64_t n_send = 0;
   bool halo_ready = false;
 
+  // in-situ SpMV launch timing (fvb_set_profiling)
+  int prof_stride = 0;
+  int64_t prof_seen = 0;
+  int prof_count = 0;
+  cudaEvent_t prof_ev[128] = {};
+
   fvb_timings tm = {};
 };

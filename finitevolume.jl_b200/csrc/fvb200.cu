@@ -134,12 +134,18 @@ int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot) 
   if (n == 0) return FVB_OK;
   const int grid = cdiv(n, kSpmvRows);
   const int fin = h->nranks == 1 ? 1 : 0;
+  int sample = -1;
+  if (dot && h->prof_stride > 0 && h->prof_count < 64 && (h->prof_seen++ % h->prof_stride) == 0) {
+    sample = h->prof_count++;
+    cudaEventRecord(h->prof_ev[2 * sample], h->stream);
+  }
   if (dot)
     k_spmv<true><<<grid, kSpmvRows, 0, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
                                                      h->partials, h->ticket, h->scal, fin);
   else
     k_spmv<false><<<grid, kSpmvRows, 0, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
                                                       h->partials, h->ticket, h->scal, fin);
+  if (sample >= 0) cudaEventRecord(h->prof_ev[2 * sample + 1], h->stream);
   h->tm.kernel_launches++;
   return FVB_OK;
 }
@@ -152,6 +158,8 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
   const int fin = h->nranks == 1 ? 1 : 0;
   const int vg = vgrid(h, n);
   FVB_TRY(ensure_hist(h, maxiter));
+  h->prof_seen = 0;
+  h->prof_count = 0;
   k_set_scal<<<1, 1, 0, st>>>(h->scal, rtol, (long long)maxiter, (long long)h->hist_cap);
   k_make_dinv<<<vg, kBlock, 0, st>>>(n, h->diag, h->Dvec, sigma, h->dinv);
   h->tm.kernel_launches += 2;
@@ -209,6 +217,15 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
   FVB_CUDA(cudaMemcpy(&h->scal_host[0], h->scal, sizeof(PcgScal), cudaMemcpyDeviceToHost));
   if (iters) *iters = h->scal_host[0].iter;
   if (converged) *converged = h->scal_host[0].converged;
+  h->tm.spmv_ms_total = 0;
+  h->tm.spmv_samples = 0;
+  for (int k = 0; k < h->prof_count; ++k) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[2 * k], h->prof_ev[2 * k + 1]) == cudaSuccess) {
+      h->tm.spmv_ms_total += ms;
+      h->tm.spmv_samples++;
+    }
+  }
   FVB_CUDA(cudaGetLastError());
   return FVB_OK;
 }
@@ -273,6 +290,7 @@ int fvb_destroy(fvb_handle h) {
   dfree(h->scal); dfree(h->ticket);
   if (h->scal_host) cudaFreeHost(h->scal_host);
   for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+  for (auto &ev : h->prof_ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return FVB_OK;
@@ -845,6 +863,15 @@ int fvb_time_spmv(fvb_handle h, int warmup, int reps, double *ms_avg) {
   float ms = 0;
   FVB_CUDA(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]));
   *ms_avg = (double)ms / reps;
+  return FVB_OK;
+}
+
+int fvb_set_profiling(fvb_handle h, int stride) {
+  FVB_TRY(check_handle(h, false));
+  if (stride < 0) return set_error(FVB_ERR_BAD_INPUT, "stride must be >= 0");
+  if (stride > 0 && !h->prof_ev[0])
+    for (auto &ev : h->prof_ev) FVB_CUDA(cudaEventCreate(&ev));
+  h->prof_stride = stride;
   return FVB_OK;
 }
 

@@ -166,9 +166,13 @@ int fvb_time_spmv(fvb_handle h, int warmup, int reps, double *ms_avg);
 /* Device times of the phases of the last fvb_assemble / fvb_solve on this handle. */
 typedef struct {
   double h2d_ms, assemble_ms, solve_ms, d2h_ms;
-  double spmv_ms_total;    /* sum of SpMV kernel time inside the last solve, if profiled */
+  double spmv_ms_total;    /* summed device time of the SpMV launches sampled in the last solve */
+  int64_t spmv_samples;    /* how many launches that sum covers (0 when profiling is off)      */
   int64_t kernel_launches; /* kernels launched by the library since fvb_create */
 } fvb_timings;
+/* Bracket every `stride`-th SpMV launch of subsequent solves with CUDA events (at most 64
+ * samples per solve); 0 switches it off.  Costs two event records per sampled launch. */
+int fvb_set_profiling(fvb_handle h, int stride);
 int fvb_get_timings(fvb_handle h, fvb_timings *out);
 int fvb_sync(fvb_handle h);
 
