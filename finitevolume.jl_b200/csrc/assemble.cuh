@@ -295,6 +295,12 @@ __global__ void k_row_values(int nf_local, const int *__restrict__ adjptr, const
   }
 }
 
+// rowptr[n+1 .. n+pad] = rowptr[n]: tiles that run past the last row see empty rows.
+__global__ void k_fill_tail(int *rowptr, int n, int pad) {
+  const int v = rowptr[n];
+  for (int i = threadIdx.x; i < pad; i += blockDim.x) rowptr[n + 1 + i] = v;
+}
+
 // ---- extraction to the Julia layout ---------------------------------------------------------------
 __global__ void k_export_ptr(const int *__restrict__ rowptr, int64_t n1, int64_t *__restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

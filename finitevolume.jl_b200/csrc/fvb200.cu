@@ -132,18 +132,19 @@ int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot) 
   FVB_TRY(halo_exchange(h, vec));
   const int n = (int)h->nf_local;
   if (n == 0) return FVB_OK;
-  const int grid = cdiv(n, kSpmvRows);
+  const int grid = std::min(cdiv(n, kSpmvRows), h->num_sms * kSpmvCtasPerSm);
   const int fin = h->nranks == 1 ? 1 : 0;
+  const size_t smem = sizeof(SpmvSmem);
   int sample = -1;
   if (dot && h->prof_stride > 0 && h->prof_count < 64 && (h->prof_seen++ % h->prof_stride) == 0) {
     sample = h->prof_count++;
     cudaEventRecord(h->prof_ev[2 * sample], h->stream);
   }
   if (dot)
-    k_spmv<true><<<grid, kSpmvRows, 0, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
+    k_spmv<true><<<grid, kSpmvThreads, smem, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
                                                      h->partials, h->ticket, h->scal, fin);
   else
-    k_spmv<false><<<grid, kSpmvRows, 0, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
+    k_spmv<false><<<grid, kSpmvThreads, smem, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
                                                       h->partials, h->ticket, h->scal, fin);
   if (sample >= 0) cudaEventRecord(h->prof_ev[2 * sample + 1], h->stream);
   h->tm.kernel_launches++;
@@ -274,6 +275,8 @@ int fvb_create(int device, fvb_handle *out) {
   FVB_CUDA(cudaMemset(h->ticket, 0, 4 * sizeof(unsigned int)));
   FVB_CUDA(cudaMemset(h->scal, 0, sizeof(PcgScal)));
   FVB_CUDA(cudaMallocHost((void **)&h->scal_host, 2 * sizeof(PcgScal)));
+  FVB_CUDA(cudaFuncSetAttribute(k_spmv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
+  FVB_CUDA(cudaFuncSetAttribute(k_spmv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
   *out = h;
   return FVB_OK;
 }
@@ -488,12 +491,14 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
 
   // ---- 4. row structure, 5. values ------------------------------------------------------------------
   ColKey key{nf_local, h->row_start, h->halo_glob};
-  A_TRY(dalloc(&h->rowptr, (int64_t)nf_local + 1));
+  A_TRY(dalloc(&h->rowptr, (int64_t)nf_local + 1 + kRowptrPad));
   if (nf_local) {
     k_row_structure<<<grid_for(nf_local), kBlock, 0, st>>>(nf_local, h->adjptr, h->adj_face, h->adj_col, key, d_cnt);
     h->tm.kernel_launches++;
   }
   exclusive_scan(d_cnt, nf_local, h->rowptr, d_scratch, st, &h->tm.kernel_launches);
+  k_fill_tail<<<1, kBlock, 0, st>>>(h->rowptr, nf_local, kRowptrPad);  // spare entries = nnz (empty rows)
+  h->tm.kernel_launches++;
   int nnz = 0;
   int herr[ERR_COUNT];
   A_CUDA(cudaMemcpyAsync(&nnz, h->rowptr + nf_local, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -516,8 +521,10 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
     return set_error(FVB_ERR_BAD_INPUT, "metaindex(" + std::to_string(herr[ERR_BAD_META] + 1) + ") is outside conductivities");
   }
   h->nnz = nnz;
-  A_TRY(dalloc(&h->colidx, nnz));
-  A_TRY(dalloc(&h->vals, nnz));
+  A_TRY(dalloc(&h->colidx, (int64_t)nnz + kCsrPad));
+  A_TRY(dalloc(&h->vals, (int64_t)nnz + kCsrPad));
+  A_CUDA(cudaMemsetAsync(h->colidx + nnz, 0, sizeof(int) * kCsrPad, st));
+  A_CUDA(cudaMemsetAsync(h->vals + nnz, 0, sizeof(double) * kCsrPad, st));
   A_TRY(dalloc(&h->b, nf_local));
   A_TRY(dalloc(&h->diag, nf_local));
   if (nf_local) {
