@@ -45,11 +45,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=512, help="grid points per axis (BASELINE metric: 512)")
+    ap.add_argument("--grid", dest="n", type=int, default=512, help="grid points per axis (BASELINE metric: 512)")
     ap.add_argument("--sigma", type=float, default=1.0, help="std of ln K (lognormal conductivity)")
     ap.add_argument("--rtol", type=float, default=SQRT_EPS)
     ap.add_argument("--maxiter", type=int, default=200000)
-    ap.add_argument("--cpu-sample-n", type=int, default=96, help="grid size of the bounded CPU sample")
+    ap.add_argument("--cpu-sample-n", type=int, default=160, help="grid size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1)
     return ap.parse_args()

@@ -1,0 +1,87 @@
+"""Worker for tests/test_gpu_multi.py: run under torchrun with one rank per GPU.
+Slab-partitioned assemble + Jacobi-PCG over NCCL, checked on rank 0 against the CPU oracle."""
+import importlib
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    fv = g.load_package()
+    fvd = importlib.import_module("fvb200.distributed")
+    ns = [int(v) for v in os.environ.get("FV_NS", "20,12,10").split(",")]
+    N = int(np.prod(ns))
+    plane = ns[1] * ns[2]
+    planes = fvd.slab_planes(ns[0], world)
+    lo, hi = fvd.node_range_of_planes(planes[rank], ns[1], ns[2])
+    maxs = [n - 1 for n in ns]
+    _, nb, aol, vol = fv.regulargrid([0, 0, 0], maxs, ns, want_coords=False, planes=planes[rank] if world > 1 else None)
+    lnk = math.log(1e-5) + np.random.default_rng(0).standard_normal(N)
+    kf = 0.5 * (lnk[nb[:, 0] - 1] + lnk[nb[:, 1] - 1])
+    dn = np.concatenate([np.arange(1, plane + 1), np.arange(N - plane + 1, N + 1)])
+    dh = np.concatenate([np.ones(plane), np.zeros(plane)])
+    src_all = 1e-7 * np.random.default_rng(1).standard_normal(N)
+    src_all[dn - 1] = 0
+    s = fv.System(local)
+    fvd.init_comm(s)
+    s.assemble(nb, aol, kf, src_all[lo - 1:hi], dn, dh, None, True, n_nodes=N, node_range=(lo, hi))
+    fvd.exchange_halo_plan(s)
+    head, x, ch = s.solve(rtol=1e-12, want_x=True)
+    # distributed SpMV of a known vector
+    sz = s.sizes()
+    xg = np.sin(np.arange(sz["nf_global"]) * 0.37) + 2.0
+    y_loc = s.spmv(xg[sz["row_start"] - 1: sz["row_start"] - 1 + sz["nf_local"]])
+    # transient step across ranks (diffnorm is a global reduction)
+    s.set_storage(0.1, vol)
+    s.vec_load_b(0)
+    s.vec_upload(1, np.full(sz["nf_local"], 0.5))
+    it_t, conv_t = s.step(0, 1, 25.0, 2, rtol=1e-12)
+    dnorm = s.vec_diffnorm(1, 2)
+    step_loc = s.vec_download(2)
+    out = [None] * world
+    dist.all_gather_object(out, (head, y_loc, ch.iters, ch.isconverged, step_loc, dnorm, conv_t))
+    ok = True
+    if rank == 0:
+        from oracle import fv_oracle as orc
+        _, nbg, aolg, volg = orc.regulargrid([0, 0, 0], maxs, ns, want_coords=False)
+        kfg = orc.nodehycos2neighborhycos(nbg, lnk, True)
+        ho, cho, Ao, bo, fn = orc.solvediffusion(nbg, aolg, kfg, src_all, dn, dh, maxiter=50000, tol=1e-12,
+                                                 logtransformconductivity=True)
+        hg = np.concatenate([o[0] for o in out])
+        yg = np.concatenate([o[1] for o in out])
+        err_h = np.max(np.abs(hg - ho)) / np.max(np.abs(ho))
+        err_y = np.max(np.abs(yg - orc.spmv(Ao, xg)) / (np.abs(orc.spmv(Ao, xg)) + 1e-300))
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+        D = 0.1 * volg[fn]
+        M = (sp.diags(1 / D) @ Ao.toscipy().tocsr() + sp.identity(D.size) / 25.0).tocsc()
+        ref = spla.spsolve(M, bo / D + 0.5 / 25.0)
+        sg = np.concatenate([o[4] for o in out])
+        err_s = np.max(np.abs(sg - ref)) / np.max(np.abs(ref))
+        dn_ref = np.linalg.norm(sg - 0.5)
+        iters = {o[2] for o in out}
+        ok = (err_h <= 1e-8 and err_y <= 1e-12 and err_s <= 1e-8 and len(iters) == 1 and all(o[3] for o in out)
+              and abs(out[0][5] - dn_ref) <= 1e-10 * dn_ref and all(o[6] for o in out)
+              and abs(out[0][2] - cho.iters) <= 3)
+        print(f"MGPU world={world} ns={ns} err_head={err_h:.2e} err_spmv={err_y:.2e} err_step={err_s:.2e} "
+              f"iters={sorted(iters)} oracle_iters={cho.iters} ok={ok}", flush=True)
+    flag = [ok]
+    dist.broadcast_object_list(flag, src=0)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if flag[0] else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
