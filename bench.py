@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--sigma", type=float, default=1.0, help="std of ln K (lognormal conductivity)")
     ap.add_argument("--rtol", type=float, default=SQRT_EPS)
     ap.add_argument("--maxiter", type=int, default=200000)
-    ap.add_argument("--cpu-sample-n", type=int, default=160, help="grid size of the bounded CPU sample")
+    ap.add_argument("--cpu-sample-n", type=int, default=192, help="grid size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1)
     return ap.parse_args()

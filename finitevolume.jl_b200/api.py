@@ -261,6 +261,16 @@ class System:
         check(lib().fvb_time_spmv(self._h, C.c_int(warmup), C.c_int(reps), C.byref(out)))
         return out.value
 
+    def set_spmv_format(self, fmt):
+        """0 = automatic (diagonal copy when the pattern allows), 1 = always CSR."""
+        check(lib().fvb_set_spmv_format(self._h, C.c_int(int(fmt))))
+
+    def spmv_format(self):
+        """-> ("csr" | "dia", number of positive offsets)."""
+        a, k = C.c_int(), C.c_int()
+        check(lib().fvb_get_spmv_format(self._h, C.byref(a), C.byref(k)))
+        return ("dia" if a.value == 2 else "csr"), k.value
+
     def set_profiling(self, stride):
         check(lib().fvb_set_profiling(self._h, C.c_int(int(stride))))
 

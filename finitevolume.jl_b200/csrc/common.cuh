@@ -101,6 +101,14 @@ struct fvb_handle_s {
   int64_t n_send = 0;
   bool halo_ready = false;
 
+  // index-free diagonal copy of A (dia.cuh), built when the pattern allows
+  int fmt_request = 0;          // 0 auto, 1 CSR only
+  bool dia_on = false;
+  int dia_K = 0;
+  int64_t dia_off[4] = {};
+  double *dia_U[4] = {};
+  int64_t dia_lo0 = 0, dia_nlo = 0, dia_hi0 = 0, dia_nhi = 0;
+
   // in-situ SpMV launch timing (fvb_set_profiling)
   int prof_stride = 0;
   int64_t prof_seen = 0;

@@ -9,6 +9,7 @@
 
 #include "assemble.cuh"
 #include "common.cuh"
+#include "dia.cuh"
 #include "nccl_dyn.h"
 #include "pcg.cuh"
 #include "scan.cuh"
@@ -61,6 +62,9 @@ void free_problem(fvb_handle h) {
   for (auto &s : h->slots) dfree(s);
   dfree(h->partials); dfree(h->hist); dfree(h->xio); dfree(h->yio);
   dfree(h->send_rows); dfree(h->sendbuf);
+  for (auto &u : h->dia_U) dfree(u);
+  h->dia_on = false;
+  h->dia_K = 0;
   h->hist_cap = 0;
   h->assembled = false;
   h->halo_ready = false;
@@ -140,13 +144,113 @@ int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot) 
     sample = h->prof_count++;
     cudaEventRecord(h->prof_ev[2 * sample], h->stream);
   }
-  if (dot)
+  if (h->dia_on && h->fmt_request != 1) {
+    DiaDesc D;
+    D.K = h->dia_K;
+    for (int k = 0; k < kDiaMaxOff; ++k) { D.off[k] = h->dia_off[k]; D.U[k] = h->dia_U[k]; }
+    D.diag = h->diag; D.row_start = h->row_start; D.nf = h->nf_local;
+    D.lo0 = h->dia_lo0; D.nlo = h->dia_nlo; D.hi0 = h->dia_hi0; D.nhi = h->dia_nhi;
+    const int dg = std::min(cdiv(n, kBlock * kDiaRowsPerThread), h->num_sms * kDiaCtasPerSm);
+#define FVB_DIA_LAUNCH(DOTV, KV)                                                                              \
+  k_spmv_dia<DOTV, KV><<<dg, kBlock, 0, h->stream>>>(n, D, vec, out, h->Dvec, sigma, h->partials, h->ticket, \
+                                                     h->scal, fin)
+#define FVB_DIA_K(DOTV)                                   \
+  switch (D.K) {                                          \
+    case 1: FVB_DIA_LAUNCH(DOTV, 1); break;               \
+    case 2: FVB_DIA_LAUNCH(DOTV, 2); break;               \
+    case 3: FVB_DIA_LAUNCH(DOTV, 3); break;               \
+    default: FVB_DIA_LAUNCH(DOTV, 4); break;              \
+  }
+    if (dot) { FVB_DIA_K(true) } else { FVB_DIA_K(false) }
+#undef FVB_DIA_K
+#undef FVB_DIA_LAUNCH
+  } else if (dot)
     k_spmv<true><<<grid, kSpmvThreads, smem, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
                                                      h->partials, h->ticket, h->scal, fin);
   else
     k_spmv<false><<<grid, kSpmvThreads, smem, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
                                                       h->partials, h->ticket, h->scal, fin);
   if (sample >= 0) cudaEventRecord(h->prof_ev[2 * sample + 1], h->stream);
+  h->tm.kernel_launches++;
+  return FVB_OK;
+}
+
+// Try to mirror A onto <= kDiaMaxOff symmetric diagonals (dia.cuh).  structure=true: detect the
+// pattern and allocate; false: only refresh the values (fvb_update_values).
+int build_dia(fvb_handle h, bool structure) {
+  cudaStream_t st = h->stream;
+  const int n = (int)h->nf_local;
+  if (structure) {
+    for (auto &u : h->dia_U) dfree(u);
+    h->dia_on = false;
+    h->dia_K = 0;
+    if (n < 2 || h->nnz == 0) return FVB_OK;
+    FVB_CUDA(cudaStreamSynchronize(st));  // the sample reads below go through the blocking default stream
+    // candidate offsets: the union over a few sample rows (first, quartiles, last)
+    std::vector<int64_t> offs;
+    std::vector<int> rp(2), cols;
+    const int samples[5] = {0, n / 4, n / 2, (int)((int64_t)3 * n / 4), n - 1};
+    for (int sr : samples) {
+      FVB_CUDA(cudaMemcpy(rp.data(), h->rowptr + sr, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+      int len = rp[1] - rp[0];
+      if (len > 64) return FVB_OK;
+      cols.resize((size_t)std::max(len, 1));
+      if (len) FVB_CUDA(cudaMemcpy(cols.data(), h->colidx + rp[0], sizeof(int) * (size_t)len, cudaMemcpyDeviceToHost));
+      for (int k = 0; k < len; ++k) {
+        int64_t g = cols[(size_t)k] < n ? h->row_start + cols[(size_t)k] : h->halo_host[(size_t)(cols[(size_t)k] - n)];
+        int64_t d = g - (h->row_start + sr);
+        if (d < 0) d = -d;
+        if (d != 0 && std::find(offs.begin(), offs.end(), d) == offs.end()) offs.push_back(d);
+      }
+    }
+    std::sort(offs.begin(), offs.end());
+    const int K = (int)offs.size();
+    if (K == 0 || K > kDiaMaxOff) return FVB_OK;
+    if ((double)h->nnz < 0.5 * (2.0 * K + 1.0) * n) return FVB_OK;  // mostly empty diagonals: CSR is smaller
+    // halo columns must form at most one contiguous run below and one above the owned rows
+    int64_t lo0 = 0, nlo = 0, hi0 = 0, nhi = 0;
+    for (int64_t g : h->halo_host) {
+      if (g < h->row_start) {
+        if (nlo == 0) lo0 = g;
+        if (g != lo0 + nlo) return FVB_OK;
+        ++nlo;
+      } else {
+        if (nhi == 0) hi0 = g;
+        if (g != hi0 + nhi) return FVB_OK;
+        ++nhi;
+      }
+    }
+    int64_t o[4] = {0, 0, 0, 0};
+    for (int k = 0; k < K; ++k) o[k] = offs[(size_t)k];
+    int *d_flag = nullptr;
+    FVB_TRY(dalloc(&d_flag, 1));
+    cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+    k_dia_check<<<grid_for(n), kBlock, 0, st>>>(n, h->rowptr, h->colidx, n, h->row_start, h->halo_glob, K, o[0], o[1],
+                                                o[2], o[3], d_flag);
+    h->tm.kernel_launches++;
+    int flag = 1;
+    cudaError_t e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    dfree(d_flag);
+    if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+    if (flag) return FVB_OK;
+    for (int k = 0; k < K; ++k) {
+      if (dalloc(&h->dia_U[k], (int64_t)n + o[k]) != FVB_OK) {  // not enough memory: stay on CSR
+        for (auto &u : h->dia_U) dfree(u);
+        return FVB_OK;
+      }
+      h->dia_off[k] = o[k];
+    }
+    h->dia_K = K;
+    h->dia_lo0 = lo0; h->dia_nlo = nlo; h->dia_hi0 = hi0; h->dia_nhi = nhi;
+    h->dia_on = true;
+  }
+  if (!h->dia_on) return FVB_OK;
+  for (int k = 0; k < h->dia_K; ++k)
+    FVB_CUDA(cudaMemsetAsync(h->dia_U[k], 0, sizeof(double) * (size_t)(n + h->dia_off[k]), st));
+  k_dia_fill<<<grid_for(n), kBlock, 0, st>>>(n, h->rowptr, h->colidx, h->vals, n, h->row_start, h->halo_glob, h->dia_K,
+                                             h->dia_off[0], h->dia_off[1], h->dia_off[2], h->dia_off[3], h->dia_U[0],
+                                             h->dia_U[1], h->dia_U[2], h->dia_U[3]);
   h->tm.kernel_launches++;
   return FVB_OK;
 }
@@ -533,6 +637,7 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
                                                         h->vals, h->diag, h->b, 1);
     h->tm.kernel_launches++;
   }
+  if (h->fmt_request != 1) A_TRY(build_dia(h, true));
   A_CUDA(cudaEventRecord(h->ev[2], st));
   A_CUDA(cudaStreamSynchronize(st));
   A_CUDA(cudaGetLastError());
@@ -575,6 +680,7 @@ int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk
                                                            h->colidx, h->vals, h->diag, h->b, 0);
     h->tm.kernel_launches++;
   }
+  if (h->dia_on) build_dia(h, false);
   cudaEventRecord(h->ev[2], st);
   int herr[ERR_COUNT];
   cudaMemcpyAsync(herr, d_err, sizeof(herr), cudaMemcpyDeviceToHost, st);
@@ -870,6 +976,22 @@ int fvb_time_spmv(fvb_handle h, int warmup, int reps, double *ms_avg) {
   float ms = 0;
   FVB_CUDA(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]));
   *ms_avg = (double)ms / reps;
+  return FVB_OK;
+}
+
+int fvb_set_spmv_format(fvb_handle h, int fmt) {
+  FVB_TRY(check_handle(h, false));
+  if (fmt != 0 && fmt != 1) return set_error(FVB_ERR_BAD_INPUT, "format must be 0 (auto) or 1 (CSR)");
+  h->fmt_request = fmt;
+  if (fmt == 0 && h->assembled && !h->dia_on) FVB_TRY(build_dia(h, true));
+  return FVB_OK;
+}
+
+int fvb_get_spmv_format(fvb_handle h, int *active, int *n_offsets) {
+  FVB_TRY(check_handle(h, true));
+  const bool dia = h->dia_on && h->fmt_request != 1;
+  if (active) *active = dia ? 2 : 1;
+  if (n_offsets) *n_offsets = dia ? h->dia_K : 0;
   return FVB_OK;
 }
 

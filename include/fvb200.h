@@ -159,6 +159,15 @@ int fvb_step(fvb_handle h, int rhs_slot, int u_slot, double dt, int out_slot, in
 /* Scatter a free-row slot to owned nodes (freenodes2nodes, src/transient.jl:172). */
 int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes);
 
+/* ---- SpMV storage format ---------------------------------------------------------------
+ * After assembly the library checks whether every entry of A lies on at most 4 symmetric
+ * diagonals (regulargrid numbering, src/grid.jl:60); if so the solver streams an index-free
+ * symmetric-diagonal copy (8*(K+1)+16 bytes per row) instead of the CSR arrays
+ * (12*nnz_row+20).  The CSR arrays stay resident either way (fvb_get_csr).
+ *   fmt: 0 = automatic (default), 1 = always CSR.   active: 1 = CSR, 2 = diagonal. */
+int fvb_set_spmv_format(fvb_handle h, int fmt);
+int fvb_get_spmv_format(fvb_handle h, int *active, int *n_offsets);
+
 /* ---- measurement hooks (CUDA events on the handle's own stream) ------------------- */
 /* Average device time of one SpMV launch (K5) / one PCG iteration over `reps` launches
  * on resident data, after `warmup` untimed ones. */

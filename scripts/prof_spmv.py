@@ -18,8 +18,15 @@ t0 = time.perf_counter()
 s.assemble(P["nb"], P["aol"], P["kf"], P["src"], P["dn"], P["dh"], None, True)
 t1 = time.perf_counter()
 sz = s.sizes()
+fmt = s.spmv_format()
+s.set_spmv_format(1)
 ms = s.time_spmv(warmup=2, reps=5)
+s.set_spmv_format(0)
+ms_auto = s.time_spmv(warmup=2, reps=5)
 gb = spmv_bytes(sz["nf_local"], sz["nnz_local"]) / 1e9
+gb_dia = (8 * (fmt[1] + 1) + 16) * sz["nf_local"] / 1e9
+print(f"format(auto)={fmt} spmv(auto)={ms_auto:.4f} ms -> {gb_dia / ms_auto * 1e3:.1f} GB/s of its own bytes, "
+      f"{gb / ms_auto * 1e3:.1f} GB/s CSR-equivalent")
 print(f"n={n} Nf={sz['nf_local']} nnz={sz['nnz_local']} assemble(wall incl. H2D)={t1 - t0:.3f}s "
       f"tm={s.timings()} spmv={ms:.4f} ms -> {gb / ms * 1e3:.1f} GB/s")
 head, x, ch = s.solve(maxiter=iters)

@@ -379,3 +379,70 @@ def test_theis_transient(fv, orc):
                                           P["dn"], P["dh"], atol=1e-4, dt0=60.0)
     assert np.allclose(ts, tso, rtol=0, atol=0)
     assert np.max(np.abs(us[-1] - uso[-1])) <= 1e-6
+
+
+def test_diagonal_format_matches_csr(fv, orc, fourfractures):
+    """The index-free symmetric-diagonal copy is picked for regulargrid numbering and must give the
+    same products and the same solve as the CSR kernel; irregular graphs stay on CSR."""
+    nb, aol, lnkf, src, dn, dh, vol = box_problem(fv, [18, 11, 7], 1.5)
+    src = 1e-6 * np.random.default_rng(3).standard_normal(src.size)
+    src[dn - 1] = 0
+    s = fv.System().assemble(nb, aol, lnkf, src, dn, dh, None, True)
+    assert s.spmv_format() == ("dia", 3)
+    x = np.random.default_rng(9).standard_normal(s.sizes()["nf_local"])
+    y_dia = s.spmv(x)
+    head_dia, _, ch_dia = s.solve(rtol=RT_TIGHT)
+    s.set_spmv_format(1)
+    assert s.spmv_format() == ("csr", 0)
+    y_csr = s.spmv(x)
+    head_csr, _, ch_csr = s.solve(rtol=RT_TIGHT)
+    assert np.array_equal(y_dia, y_csr)  # same products, same (column) summation order
+    # the fused u.Au partials are grouped differently by the two kernels: equal to rounding only
+    assert abs(ch_dia.iters - ch_csr.iters) <= 1 and np.allclose(head_dia, head_csr, rtol=1e-9, atol=1e-12)
+    Ao = orc.assembleA(nb, aol, lnkf, src, dn, dh, None, True)
+    assert np.allclose(y_dia, orc.spmv(Ao, x), rtol=1e-13, atol=1e-20)
+    s.set_spmv_format(0)
+    assert s.spmv_format() == ("dia", 3)
+    # values-only update refreshes the diagonal copy too
+    lnk2 = lnkf + 0.1
+    s.update_values(lnk2)
+    s2 = fv.System().assemble(nb, aol, lnk2, src, dn, dh, None, True)
+    s2.set_spmv_format(1)
+    assert np.array_equal(s.spmv(x), s2.spmv(x))
+    # transient operator A + D/dt on the diagonal format
+    s.set_storage(0.1, vol); s2.set_storage(0.1, vol)
+    for t in (s, s2):
+        t.vec_load_b(0); t.vec_upload(1, x)
+    it1, _ = s.step(0, 1, 13.0, 2, rtol=1e-12)
+    it2, _ = s2.step(0, 1, 13.0, 2, rtol=1e-12)
+    assert abs(it1 - it2) <= 1 and np.allclose(s.vec_download(2), s2.vec_download(2), rtol=1e-9, atol=1e-12)
+    # a 1-D chain is a single diagonal; the fracture graph and circular Dirichlet regions are not
+    chain = fv.System().assemble([(i, i + 1) for i in range(1, 400)], np.ones(399), np.ones(399), np.zeros(400),
+                                 [1, 400], [1.0, 0.0])
+    assert chain.spmv_format() == ("dia", 1)
+    hc, _, chc = chain.solve(rtol=1e-13)
+    assert chc.isconverged and np.allclose(hc, np.linspace(1, 0, 400), atol=1e-9)
+    m = fourfractures
+    frac = fv.System().assemble(m["neighbors"], m["areasoverlengths"], m["conductivities"], np.zeros(m["xs"].size),
+                                m["dirichletnodes"], m["dirichletheads"])
+    assert frac.spmv_format()[0] == "csr"
+
+
+def test_diagonal_format_on_slabs(fv):
+    """Slab parts reference halo columns; their diagonal copies must agree with their CSR rows
+    (halo x entries are zero on an unconnected handle, which both kernels must honour)."""
+    import importlib
+    dist = importlib.import_module("fvb200.distributed")
+    ns = [8, 5, 4]
+    nb, aol, lnkf, src, dn, dh, _ = box_problem(fv, ns, 1.0)
+    N = src.size
+    for pl in dist.slab_planes(ns[0], 3):
+        lo, hi = dist.node_range_of_planes(pl, ns[1], ns[2])
+        touch = ((nb[:, 0] >= lo) & (nb[:, 0] <= hi)) | ((nb[:, 1] >= lo) & (nb[:, 1] <= hi))
+        s = fv.System().assemble(nb[touch], aol[touch], lnkf[touch], src[lo - 1:hi], dn, dh, None, True, n_nodes=N,
+                                 node_range=(lo, hi))
+        assert s.spmv_format() == ("dia", 3)
+        x = np.random.default_rng(1).standard_normal(s.sizes()["nf_local"])
+        y1 = s.spmv(x)
+        s.set_spmv_format(1)
+        assert np.array_equal(y1, s.spmv(x))
