@@ -287,13 +287,19 @@ def main():
         if world > 1:
             dist.barrier()
 
+    wall_parts = {}
+
     def step(src_arrays, head_ptr):
         a = src_arrays
+        t0 = time.perf_counter()
         sysm.assemble_raw(P["N"], lo, hi, P["F"], a["nb"], a["aol"], a["kf"], P["F"], 0, True, a["src"],
                           P["dn"].size, a["dn"], a["dh"])
+        t1 = time.perf_counter()
         if world > 1:
             fvd.exchange_halo_plan(sysm)
+        t2 = time.perf_counter()
         it, conv = sysm.solve_raw(args.rtol, args.maxiter, head_ptr=head_ptr)
+        wall_parts.update(assemble_call_s=t1 - t0, halo_plan_s=t2 - t1, solve_call_s=time.perf_counter() - t2)
         return it, conv
 
     dev_ptrs = {k: v.data_ptr() for k, v in dev.items()}
@@ -339,13 +345,18 @@ def main():
     barrier()
     e2e_s = maxreduce((time.perf_counter() - e0) / max(args.e2e_steps, 1))
     e2e_tm = sysm.timings()
+    e2e_parts = dict(wall_parts)
 
     # sanity of the result that was timed: maximum principle + convergence (not a parity test)
     hh = head_host.numpy()
     ok = bool(conv and conv_e and hh.min() >= -1e-6 and hh.max() <= 1 + 1e-6)
 
     spmv_avg_ms = spmv_ms / max(spmv_samples, 1)
-    alg_bytes = spmv_bytes(sz["nf_local"], sz["nnz_local"])
+    fmt, fmt_k = sysm.spmv_format()
+    csr_bytes = spmv_bytes(sz["nf_local"], sz["nnz_local"])
+    # an index-free diagonal format is reported against ITS algorithmic bytes
+    # (8 per stored diagonal entry incl. the main diagonal, x read once, y written once)
+    alg_bytes = (8 * (fmt_k + 1) + 16) * sz["nf_local"] if fmt == "dia" else csr_bytes
     achieved = alg_bytes / (spmv_avg_ms * 1e-3) / 1e9 if spmv_samples else None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -362,6 +373,15 @@ def main():
         except Exception:
             pass
 
+    # the general CSR kernel on the same resident matrix, timed alone (20 launches, CUDA events)
+    csr_roof = None
+    if world == 1:
+        sysm.set_spmv_format(1)
+        ms_csr = sysm.time_spmv(warmup=3, reps=20)
+        sysm.set_spmv_format(0)
+        csr_roof = {"kernel": "k_spmv<false> (CSR, TMA-staged)", "avg_launch_ms": ms_csr,
+                    "algorithmic_bytes_per_launch": int(csr_bytes), "achieved": csr_bytes / (ms_csr * 1e-3) / 1e9,
+                    "frac": csr_bytes / (ms_csr * 1e-3) / 1e9 / peak, "timed": "alone, 20 launches"}
     if world > 1:
         ach_t = torch.tensor([achieved or 0.0], dtype=torch.float64)
         dist.all_reduce(ach_t, op=dist.ReduceOp.MIN)
@@ -381,12 +401,16 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "h2d_ms": e2e_tm["h2d_ms"], "assemble_ms": e2e_tm["assemble_ms"], "solve_ms": e2e_tm["solve_ms"],
-                    "d2h_ms": e2e_tm["d2h_ms"], "pcg_iterations": it_e},
+                    "d2h_ms": e2e_tm["d2h_ms"], "pcg_iterations": it_e, "host_wall": e2e_parts},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_spmv<true> (CSR SpMV + fused u.Au)", "achieved": achieved,
+            "roofline": {"bound": "hbm",
+                         "kernel": ("k_spmv_dia<true,%d> (symmetric-diagonal SpMV + fused u.Au)" % fmt_k) if fmt == "dia"
+                         else "k_spmv<true> (CSR SpMV + fused u.Au)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
-                         "avg_launch_ms": spmv_avg_ms, "launches_sampled": int(spmv_samples),
+                         "avg_launch_ms": spmv_avg_ms, "launches_sampled": int(spmv_samples), "format": fmt,
+                         "csr_equivalent_gbs": (csr_bytes / (spmv_avg_ms * 1e-3) / 1e9) if spmv_samples else None,
+                         "csr_kernel": csr_roof,
                          "note": "rank-local rows; min over ranks" if world > 1 else "sampled inside the timed solves"},
             "cpu_baseline": cpu,
             "pcg_iterations": it, "converged": bool(conv), "result_sane": ok,

@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
+#include <cstdlib>
 
 #include "assemble.cuh"
 #include "common.cuh"
@@ -34,35 +36,45 @@ using namespace fvb;
 
 namespace {
 
+// Stream-ordered allocation from the device's memory pool (release threshold = keep everything):
+// repeated assemblies of the same size -- inverse loops, the bench -- reuse the blocks instead of
+// paying synchronous cudaMalloc/cudaFree (a quarter of a second per step at 512^3).
 template <typename T>
-int dalloc(T **p, int64_t n) {
+int dalloc(fvb_handle h, T **p, int64_t n) {
   *p = nullptr;
   size_t bytes = sizeof(T) * (size_t)std::max<int64_t>(n, 1);
-  cudaError_t e = cudaMalloc((void **)p, bytes);
+  cudaError_t e = cudaMallocAsync((void **)p, bytes, h->stream);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    return set_error(FVB_ERR_OOM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    return set_error(FVB_ERR_OOM, "cudaMallocAsync of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
   }
   return FVB_OK;
 }
 template <typename T>
-void dfree(T *&p) {
-  if (p) cudaFree(p);
+void dfree(fvb_handle h, T *&p) {
+  if (p) cudaFreeAsync(p, h->stream);
   p = nullptr;
+}
+
+// every copy goes through the handle's own stream: pool memory is ordered on it, and the handle's
+// stream is non-blocking (it does not synchronise with the legacy default stream)
+cudaError_t memcpy_sync(cudaStream_t st, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, st);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(st);
 }
 
 int grid_for(int64_t n) { return std::max(1, cdiv(n, kBlock)); }
 int vgrid(fvb_handle h, int64_t n) { return std::max(1, std::min(cdiv(n, kBlock), h->num_sms * 8)); }
 
 void free_problem(fvb_handle h) {
-  dfree(h->nodemap); dfree(h->row2node); dfree(h->sources); dfree(h->dheads); dfree(h->aol);
-  dfree(h->meta); dfree(h->cface); dfree(h->adjptr); dfree(h->adj_face); dfree(h->adj_col);
-  dfree(h->halo_glob); dfree(h->rowptr); dfree(h->colidx); dfree(h->vals); dfree(h->b); dfree(h->diag);
-  dfree(h->x); dfree(h->r); dfree(h->u); dfree(h->c); dfree(h->dinv); dfree(h->rhs); dfree(h->Dvec);
-  for (auto &s : h->slots) dfree(s);
-  dfree(h->partials); dfree(h->hist); dfree(h->xio); dfree(h->yio);
-  dfree(h->send_rows); dfree(h->sendbuf);
-  for (auto &u : h->dia_U) dfree(u);
+  dfree(h, h->nodemap); dfree(h, h->row2node); dfree(h, h->sources); dfree(h, h->dheads); dfree(h, h->aol);
+  dfree(h, h->meta); dfree(h, h->cface); dfree(h, h->adjptr); dfree(h, h->adj_face); dfree(h, h->adj_col);
+  dfree(h, h->halo_glob); dfree(h, h->rowptr); dfree(h, h->colidx); dfree(h, h->vals); dfree(h, h->b); dfree(h, h->diag);
+  dfree(h, h->x); dfree(h, h->r); dfree(h, h->u); dfree(h, h->c); dfree(h, h->dinv); dfree(h, h->rhs); dfree(h, h->Dvec);
+  for (auto &s : h->slots) dfree(h, s);
+  dfree(h, h->partials); dfree(h, h->hist); dfree(h, h->xio); dfree(h, h->yio);
+  dfree(h, h->send_rows); dfree(h, h->sendbuf);
+  for (auto &u : h->dia_U) dfree(h, u);
   h->dia_on = false;
   h->dia_K = 0;
   h->hist_cap = 0;
@@ -84,9 +96,9 @@ int check_handle(fvb_handle h, bool need_assembled) {
 int ensure_workspace(fvb_handle h) {
   const int64_t n = h->nf_local;
   if (!h->x) {
-    FVB_TRY(dalloc(&h->x, n)); FVB_TRY(dalloc(&h->r, n)); FVB_TRY(dalloc(&h->c, n));
-    FVB_TRY(dalloc(&h->u, n + h->n_halo)); FVB_TRY(dalloc(&h->dinv, n)); FVB_TRY(dalloc(&h->rhs, n));
-    FVB_TRY(dalloc(&h->partials, 2 * (int64_t)std::max(cdiv(n, kSpmvRows), h->num_sms * 8) + 2));
+    FVB_TRY(dalloc(h, &h->x, n)); FVB_TRY(dalloc(h, &h->r, n)); FVB_TRY(dalloc(h, &h->c, n));
+    FVB_TRY(dalloc(h, &h->u, n + h->n_halo)); FVB_TRY(dalloc(h, &h->dinv, n)); FVB_TRY(dalloc(h, &h->rhs, n));
+    FVB_TRY(dalloc(h, &h->partials, 2 * (int64_t)std::max(cdiv(n, kSpmvRows), h->num_sms * 8) + 2));
     FVB_CUDA(cudaMemsetAsync(h->u, 0, sizeof(double) * (size_t)std::max<int64_t>(n + h->n_halo, 1), h->stream));
   }
   return FVB_OK;
@@ -95,8 +107,8 @@ int ensure_workspace(fvb_handle h) {
 int ensure_hist(fvb_handle h, int64_t cap) {
   cap = std::max<int64_t>(std::min<int64_t>(cap, 1 << 24), 1);
   if (cap > h->hist_cap) {
-    dfree(h->hist);
-    FVB_TRY(dalloc(&h->hist, cap));
+    dfree(h, h->hist);
+    FVB_TRY(dalloc(h, &h->hist, cap));
     h->hist_cap = cap;
   }
   return FVB_OK;
@@ -181,7 +193,7 @@ int build_dia(fvb_handle h, bool structure) {
   cudaStream_t st = h->stream;
   const int n = (int)h->nf_local;
   if (structure) {
-    for (auto &u : h->dia_U) dfree(u);
+    for (auto &u : h->dia_U) dfree(h, u);
     h->dia_on = false;
     h->dia_K = 0;
     if (n < 2 || h->nnz == 0) return FVB_OK;
@@ -191,11 +203,11 @@ int build_dia(fvb_handle h, bool structure) {
     std::vector<int> rp(2), cols;
     const int samples[5] = {0, n / 4, n / 2, (int)((int64_t)3 * n / 4), n - 1};
     for (int sr : samples) {
-      FVB_CUDA(cudaMemcpy(rp.data(), h->rowptr + sr, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+      FVB_CUDA(memcpy_sync(h->stream, rp.data(), h->rowptr + sr, 2 * sizeof(int), cudaMemcpyDeviceToHost));
       int len = rp[1] - rp[0];
       if (len > 64) return FVB_OK;
       cols.resize((size_t)std::max(len, 1));
-      if (len) FVB_CUDA(cudaMemcpy(cols.data(), h->colidx + rp[0], sizeof(int) * (size_t)len, cudaMemcpyDeviceToHost));
+      if (len) FVB_CUDA(memcpy_sync(h->stream, cols.data(), h->colidx + rp[0], sizeof(int) * (size_t)len, cudaMemcpyDeviceToHost));
       for (int k = 0; k < len; ++k) {
         int64_t g = cols[(size_t)k] < n ? h->row_start + cols[(size_t)k] : h->halo_host[(size_t)(cols[(size_t)k] - n)];
         int64_t d = g - (h->row_start + sr);
@@ -223,7 +235,7 @@ int build_dia(fvb_handle h, bool structure) {
     int64_t o[4] = {0, 0, 0, 0};
     for (int k = 0; k < K; ++k) o[k] = offs[(size_t)k];
     int *d_flag = nullptr;
-    FVB_TRY(dalloc(&d_flag, 1));
+    FVB_TRY(dalloc(h, &d_flag, 1));
     cudaMemsetAsync(d_flag, 0, sizeof(int), st);
     k_dia_check<<<grid_for(n), kBlock, 0, st>>>(n, h->rowptr, h->colidx, n, h->row_start, h->halo_glob, K, o[0], o[1],
                                                 o[2], o[3], d_flag);
@@ -231,12 +243,12 @@ int build_dia(fvb_handle h, bool structure) {
     int flag = 1;
     cudaError_t e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    dfree(d_flag);
+    dfree(h, d_flag);
     if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
     if (flag) return FVB_OK;
     for (int k = 0; k < K; ++k) {
-      if (dalloc(&h->dia_U[k], (int64_t)n + o[k]) != FVB_OK) {  // not enough memory: stay on CSR
-        for (auto &u : h->dia_U) dfree(u);
+      if (dalloc(h, &h->dia_U[k], (int64_t)n + o[k]) != FVB_OK) {  // not enough memory: stay on CSR
+        for (auto &u : h->dia_U) dfree(h, u);
         return FVB_OK;
       }
       h->dia_off[k] = o[k];
@@ -319,7 +331,7 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
     if (batch < 64) batch *= 2;
   }
   FVB_CUDA(cudaStreamSynchronize(st));
-  FVB_CUDA(cudaMemcpy(&h->scal_host[0], h->scal, sizeof(PcgScal), cudaMemcpyDeviceToHost));
+  FVB_CUDA(memcpy_sync(h->stream, &h->scal_host[0], h->scal, sizeof(PcgScal), cudaMemcpyDeviceToHost));
   if (iters) *iters = h->scal_host[0].iter;
   if (converged) *converged = h->scal_host[0].converged;
   h->tm.spmv_ms_total = 0;
@@ -339,7 +351,7 @@ bool valid_slot(int s) { return s >= 0 && s < FVB_NSLOT; }
 int ensure_slot(fvb_handle h, int s) {
   if (!valid_slot(s)) return set_error(FVB_ERR_BAD_INPUT, "vector slot out of range");
   if (!h->slots[s]) {
-    FVB_TRY(dalloc(&h->slots[s], h->nf_local));
+    FVB_TRY(dalloc(h, &h->slots[s], h->nf_local));
     FVB_CUDA(cudaMemsetAsync(h->slots[s], 0, sizeof(double) * (size_t)std::max<int64_t>(h->nf_local, 1), h->stream));
   }
   return FVB_OK;
@@ -374,10 +386,17 @@ int fvb_create(int device, fvb_handle *out) {
   FVB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto &ev : h->ev) FVB_CUDA(cudaEventCreate(&ev));
   FVB_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
-  FVB_TRY(dalloc(&h->scal, 1));
-  FVB_TRY(dalloc(&h->ticket, 4));
-  FVB_CUDA(cudaMemset(h->ticket, 0, 4 * sizeof(unsigned int)));
-  FVB_CUDA(cudaMemset(h->scal, 0, sizeof(PcgScal)));
+  {
+    cudaMemPool_t pool;
+    FVB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    FVB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  FVB_TRY(dalloc(h, &h->scal, 1));
+  FVB_TRY(dalloc(h, &h->ticket, 4));
+  FVB_CUDA(cudaMemsetAsync(h->ticket, 0, 4 * sizeof(unsigned int), h->stream));
+  FVB_CUDA(cudaMemsetAsync(h->scal, 0, sizeof(PcgScal), h->stream));
+  FVB_CUDA(cudaStreamSynchronize(h->stream));
   FVB_CUDA(cudaMallocHost((void **)&h->scal_host, 2 * sizeof(PcgScal)));
   FVB_CUDA(cudaFuncSetAttribute(k_spmv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
   FVB_CUDA(cudaFuncSetAttribute(k_spmv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpmvSmem)));
@@ -394,7 +413,7 @@ int fvb_destroy(fvb_handle h) {
     if (h->comm->comm) nccl().CommDestroy(h->comm->comm);
     delete h->comm;
   }
-  dfree(h->scal); dfree(h->ticket);
+  dfree(h, h->scal); dfree(h, h->ticket);
   if (h->scal_host) cudaFreeHost(h->scal_host);
   for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
   for (auto &ev : h->prof_ev) if (ev) cudaEventDestroy(ev);
@@ -441,7 +460,15 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
   const int64_t n_own = node_hi1 - node_lo1 + 1;
   if (n_own >= INT_MAX - 1 || 2 * n_faces >= INT_MAX - 1 || nd >= INT_MAX - 1)
     return set_error(FVB_ERR_BAD_INPUT, "per-GPU part too large for 32-bit local indices; use more ranks");
+  const bool dbg = getenv("FVB_DEBUG") != nullptr;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tdbg0 = now();
+  double tdbg = tdbg0;
+  auto lap = [&](const char *what) {
+    if (dbg) { double t = now(); fprintf(stderr, "[fvb_assemble] %-28s %8.1f ms\n", what, (t - tdbg) * 1e3); tdbg = t; }
+  };
   free_problem(h);
+  lap("free previous problem");
   cudaStream_t st = h->stream;
   h->n_nodes = n_nodes; h->node_lo = node_lo1 - 1; h->node_hi = node_hi1; h->n_own_nodes = n_own;
   h->n_faces = n_faces; h->n_dirichlet = nd;
@@ -456,19 +483,19 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
   int *d_dsorted_slot = nullptr;
   unsigned long long *d_noff = nullptr;
   auto cleanup = [&]() {
-    dfree(d_nb); dfree(d_dnodes); dfree(d_cond); dfree(d_dslot); dfree(d_cnt); dfree(d_scratch); dfree(d_err);
-    dfree(d_dsorted); dfree(d_dsorted_slot); dfree(d_refs); dfree(d_noff);
+    dfree(h, d_nb); dfree(h, d_dnodes); dfree(h, d_cond); dfree(h, d_dslot); dfree(h, d_cnt); dfree(h, d_scratch); dfree(h, d_err);
+    dfree(h, d_dsorted); dfree(h, d_dsorted_slot); dfree(h, d_refs); dfree(h, d_noff);
   };
 #define A_TRY(expr) do { int s__ = (expr); if (s__ != FVB_OK) { cleanup(); free_problem(h); return s__; } } while (0)
 #define A_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); free_problem(h); \
     return set_error(FVB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
 
-  A_TRY(dalloc(&d_nb, 2 * n_faces));
-  A_TRY(dalloc(&h->aol, n_faces));
-  A_TRY(dalloc(&d_cond, n_cond));
-  A_TRY(dalloc(&h->sources, n_own));
-  A_TRY(dalloc(&d_dnodes, nd));
-  A_TRY(dalloc(&h->dheads, nd));
+  A_TRY(dalloc(h, &d_nb, 2 * n_faces));
+  A_TRY(dalloc(h, &h->aol, n_faces));
+  A_TRY(dalloc(h, &d_cond, n_cond));
+  A_TRY(dalloc(h, &h->sources, n_own));
+  A_TRY(dalloc(h, &d_dnodes, nd));
+  A_TRY(dalloc(h, &h->dheads, nd));
   A_CUDA(cudaMemcpyAsync(d_nb, neighbors, sizeof(int64_t) * 2 * (size_t)n_faces, cudaMemcpyDefault, st));
   A_CUDA(cudaMemcpyAsync(h->aol, aol, sizeof(double) * (size_t)n_faces, cudaMemcpyDefault, st));
   A_CUDA(cudaMemcpyAsync(d_cond, cond, sizeof(double) * (size_t)n_cond, cudaMemcpyDefault, st));
@@ -476,10 +503,11 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
   A_CUDA(cudaMemcpyAsync(d_dnodes, dnodes, sizeof(int64_t) * (size_t)nd, cudaMemcpyDefault, st));
   A_CUDA(cudaMemcpyAsync(h->dheads, dheads, sizeof(double) * (size_t)nd, cudaMemcpyDefault, st));
   if (metaindex) {
-    A_TRY(dalloc(&h->meta, n_faces));
+    A_TRY(dalloc(h, &h->meta, n_faces));
     A_CUDA(cudaMemcpyAsync(h->meta, metaindex, sizeof(int64_t) * (size_t)n_faces, cudaMemcpyDefault, st));
   }
   A_CUDA(cudaEventRecord(h->ev[1], st));
+  lap("alloc + enqueue H2D");
 
   // ---- Dirichlet table for off-rank endpoints (host: ND is small next to N) ---------------------
   int64_t nd_sorted = 0;
@@ -498,8 +526,8 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
       else { nodes.push_back(pr[k].first); slot.push_back(pr[k].second); }
     }
     nd_sorted = (int64_t)nodes.size();
-    A_TRY(dalloc(&d_dsorted, nd_sorted));
-    A_TRY(dalloc(&d_dsorted_slot, nd_sorted));
+    A_TRY(dalloc(h, &d_dsorted, nd_sorted));
+    A_TRY(dalloc(h, &d_dsorted_slot, nd_sorted));
     A_CUDA(cudaMemcpyAsync(d_dsorted, nodes.data(), sizeof(int64_t) * nodes.size(), cudaMemcpyHostToDevice, st));
     A_CUDA(cudaMemcpyAsync(d_dsorted_slot, slot.data(), sizeof(int) * slot.size(), cudaMemcpyHostToDevice, st));
     A_CUDA(cudaStreamSynchronize(st));
@@ -510,15 +538,15 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
   }
 
   // ---- 1. node map --------------------------------------------------------------------------
-  A_TRY(dalloc(&d_err, ERR_COUNT));
+  A_TRY(dalloc(h, &d_err, ERR_COUNT));
   {
     int init[ERR_COUNT];
     for (int &v : init) v = INT_MAX;
     A_CUDA(cudaMemcpyAsync(d_err, init, sizeof(init), cudaMemcpyHostToDevice, st));
   }
-  A_TRY(dalloc(&d_dslot, n_own));
-  A_TRY(dalloc(&d_cnt, std::max(n_own, n_faces) + 2));
-  A_TRY(dalloc(&d_scratch, scan_scratch_ints(std::max(n_own, 2 * n_faces) + 1)));
+  A_TRY(dalloc(h, &d_dslot, n_own));
+  A_TRY(dalloc(h, &d_cnt, std::max(n_own, n_faces) + 2));
+  A_TRY(dalloc(h, &d_scratch, scan_scratch_ints(std::max(n_own, 2 * n_faces) + 1)));
   A_CUDA(cudaMemsetAsync(d_dslot, 0xFF, sizeof(int) * (size_t)std::max<int64_t>(n_own, 1), st));
   if (nd) {
     k_mark_dirichlet<<<grid_for(nd), kBlock, 0, st>>>(d_dnodes, nd, n_nodes, h->node_lo, h->node_hi, h->sources,
@@ -534,16 +562,17 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
     A_CUDA(cudaStreamSynchronize(st));
   }
   h->nf_local = nf_local;
+  lap("nodemap scan (sync)");
   if (whole) h->nf_global = nf_local;
-  A_TRY(dalloc(&h->nodemap, n_own));
-  A_TRY(dalloc(&h->row2node, nf_local));
+  A_TRY(dalloc(h, &h->nodemap, n_own));
+  A_TRY(dalloc(h, &h->row2node, nf_local));
   if (n_own) {
     k_finish_nodemap<<<grid_for(n_own), kBlock, 0, st>>>(d_dslot, d_cnt, n_own, h->nodemap, h->row2node);
     h->tm.kernel_launches++;
   }
 
   // ---- 2. per-face conductance ----------------------------------------------------------------
-  A_TRY(dalloc(&h->cface, n_faces));
+  A_TRY(dalloc(h, &h->cface, n_faces));
   if (n_faces) {
     k_face_conductance<<<grid_for(n_faces), kBlock, 0, st>>>(n_faces, d_cond, n_cond, h->meta, h->aol, logk,
                                                              h->cface, d_err);
@@ -552,8 +581,8 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
 
   // ---- 3. adjacency ------------------------------------------------------------------------------
   Resolver res{h->nodemap, n_nodes, h->node_lo, h->node_hi, d_dsorted, d_dsorted_slot, nd_sorted};
-  A_TRY(dalloc(&d_noff, 1));
-  A_TRY(dalloc(&h->adjptr, (int64_t)nf_local + 1));
+  A_TRY(dalloc(h, &d_noff, 1));
+  A_TRY(dalloc(h, &h->adjptr, (int64_t)nf_local + 1));
   unsigned long long n_off = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     A_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * ((size_t)nf_local + 1), st));
@@ -566,25 +595,26 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
     A_CUDA(cudaMemcpyAsync(&n_off, d_noff, sizeof(n_off), cudaMemcpyDeviceToHost, st));
     A_CUDA(cudaStreamSynchronize(st));
     if (n_off == 0 || d_refs) break;
-    A_TRY(dalloc(&d_refs, (int64_t)n_off));  // second attempt records the references
+    A_TRY(dalloc(h, &d_refs, (int64_t)n_off));  // second attempt records the references
   }
   h->n_halo = 0;
   if (n_off) {
     h->halo_host.resize((size_t)n_off);
-    A_CUDA(cudaMemcpy(h->halo_host.data(), d_refs, sizeof(int64_t) * (size_t)n_off, cudaMemcpyDeviceToHost));
+    A_CUDA(memcpy_sync(h->stream, h->halo_host.data(), d_refs, sizeof(int64_t) * (size_t)n_off, cudaMemcpyDeviceToHost));
     std::sort(h->halo_host.begin(), h->halo_host.end());
     h->halo_host.erase(std::unique(h->halo_host.begin(), h->halo_host.end()), h->halo_host.end());
     h->n_halo = (int64_t)h->halo_host.size();
-    A_TRY(dalloc(&h->halo_glob, h->n_halo));
-    A_CUDA(cudaMemcpy(h->halo_glob, h->halo_host.data(), sizeof(int64_t) * (size_t)h->n_halo, cudaMemcpyHostToDevice));
+    A_TRY(dalloc(h, &h->halo_glob, h->n_halo));
+    A_CUDA(memcpy_sync(h->stream, h->halo_glob, h->halo_host.data(), sizeof(int64_t) * (size_t)h->n_halo, cudaMemcpyHostToDevice));
   }
   exclusive_scan(d_cnt, nf_local, h->adjptr, d_scratch, st, &h->tm.kernel_launches);
   int n_adj = 0;
   A_CUDA(cudaMemcpyAsync(&n_adj, h->adjptr + nf_local, sizeof(int), cudaMemcpyDeviceToHost, st));
   A_CUDA(cudaStreamSynchronize(st));
   h->n_adj = n_adj;
-  A_TRY(dalloc(&h->adj_face, n_adj));
-  A_TRY(dalloc(&h->adj_col, n_adj));
+  lap("adjacency count (sync)");
+  A_TRY(dalloc(h, &h->adj_face, n_adj));
+  A_TRY(dalloc(h, &h->adj_col, n_adj));
   A_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * ((size_t)nf_local + 1), st));
   if (n_faces) {
     k_adjacency<1><<<grid_for(n_faces), kBlock, 0, st>>>(n_faces, d_nb, res, d_cnt, h->adjptr, h->adj_face,
@@ -595,7 +625,7 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
 
   // ---- 4. row structure, 5. values ------------------------------------------------------------------
   ColKey key{nf_local, h->row_start, h->halo_glob};
-  A_TRY(dalloc(&h->rowptr, (int64_t)nf_local + 1 + kRowptrPad));
+  A_TRY(dalloc(h, &h->rowptr, (int64_t)nf_local + 1 + kRowptrPad));
   if (nf_local) {
     k_row_structure<<<grid_for(nf_local), kBlock, 0, st>>>(nf_local, h->adjptr, h->adj_face, h->adj_col, key, d_cnt);
     h->tm.kernel_launches++;
@@ -610,7 +640,7 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
   A_CUDA(cudaStreamSynchronize(st));
   if (herr[ERR_SRC_ON_DIRICHLET] != INT_MAX) {
     int64_t node = 0;
-    cudaMemcpy(&node, d_dnodes + herr[ERR_SRC_ON_DIRICHLET], sizeof(int64_t), cudaMemcpyDeviceToHost);
+    memcpy_sync(h->stream, &node, d_dnodes + herr[ERR_SRC_ON_DIRICHLET], sizeof(int64_t), cudaMemcpyDeviceToHost);
     cleanup(); free_problem(h);
     return set_error(FVB_ERR_BAD_INPUT, "There cannot be a source at a Dirichlet node, but node " + std::to_string(node) +
                                             " is a Dirichlet node where a source is located.");
@@ -625,12 +655,13 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
     return set_error(FVB_ERR_BAD_INPUT, "metaindex(" + std::to_string(herr[ERR_BAD_META] + 1) + ") is outside conductivities");
   }
   h->nnz = nnz;
-  A_TRY(dalloc(&h->colidx, (int64_t)nnz + kCsrPad));
-  A_TRY(dalloc(&h->vals, (int64_t)nnz + kCsrPad));
+  lap("row structure (sync)");
+  A_TRY(dalloc(h, &h->colidx, (int64_t)nnz + kCsrPad));
+  A_TRY(dalloc(h, &h->vals, (int64_t)nnz + kCsrPad));
   A_CUDA(cudaMemsetAsync(h->colidx + nnz, 0, sizeof(int) * kCsrPad, st));
   A_CUDA(cudaMemsetAsync(h->vals + nnz, 0, sizeof(double) * kCsrPad, st));
-  A_TRY(dalloc(&h->b, nf_local));
-  A_TRY(dalloc(&h->diag, nf_local));
+  A_TRY(dalloc(h, &h->b, nf_local));
+  A_TRY(dalloc(h, &h->diag, nf_local));
   if (nf_local) {
     k_row_values<<<grid_for(nf_local), kBlock, 0, st>>>(nf_local, h->adjptr, h->adj_face, h->adj_col, key, h->cface,
                                                         h->sources, h->dheads, h->row2node, h->rowptr, h->colidx,
@@ -644,7 +675,9 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->tm.h2d_ms = ms;
   cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->tm.assemble_ms = ms;
+  lap("values + dia (sync)");
   cleanup();
+  lap("free temporaries");
 #undef A_TRY
 #undef A_CUDA
   h->assembled = true;
@@ -659,8 +692,8 @@ int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk
   cudaStream_t st = h->stream;
   double *d_cond = nullptr;
   int *d_err = nullptr;
-  FVB_TRY(dalloc(&d_cond, n_cond));
-  FVB_TRY(dalloc(&d_err, ERR_COUNT));
+  FVB_TRY(dalloc(h, &d_cond, n_cond));
+  FVB_TRY(dalloc(h, &d_err, ERR_COUNT));
   int init[ERR_COUNT];
   for (int &v : init) v = INT_MAX;
   cudaMemcpyAsync(d_err, init, sizeof(init), cudaMemcpyHostToDevice, st);
@@ -685,7 +718,7 @@ int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk
   int herr[ERR_COUNT];
   cudaMemcpyAsync(herr, d_err, sizeof(herr), cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);
-  dfree(d_cond); dfree(d_err);
+  dfree(h, d_cond); dfree(h, d_err);
   if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->tm.assemble_ms = ms;
@@ -711,7 +744,7 @@ int fvb_get_csr(fvb_handle h, int64_t *ptr, int64_t *idx, double *val) {
   // export through a bounded device staging buffer (the int64 image of colidx can be 7 GiB)
   const int64_t chunk = 1 << 24;
   int64_t *d_tmp = nullptr;
-  FVB_TRY(dalloc(&d_tmp, chunk));
+  FVB_TRY(dalloc(h, &d_tmp, chunk));
   if (ptr) {
     for (int64_t o = 0; o < h->nf_local + 1; o += chunk) {
       int64_t m = std::min(chunk, h->nf_local + 1 - o);
@@ -730,19 +763,19 @@ int fvb_get_csr(fvb_handle h, int64_t *ptr, int64_t *idx, double *val) {
       FVB_CUDA(cudaStreamSynchronize(st));
     }
   }
-  dfree(d_tmp);
-  if (val) FVB_CUDA(cudaMemcpy(val, h->vals, sizeof(double) * (size_t)h->nnz, cudaMemcpyDefault));
+  dfree(h, d_tmp);
+  if (val) FVB_CUDA(memcpy_sync(h->stream, val, h->vals, sizeof(double) * (size_t)h->nnz, cudaMemcpyDefault));
   return FVB_OK;
 }
 
 int fvb_get_b(fvb_handle h, double *b) {
   FVB_TRY(check_handle(h, true));
-  FVB_CUDA(cudaMemcpy(b, h->b, sizeof(double) * (size_t)h->nf_local, cudaMemcpyDefault));
+  FVB_CUDA(memcpy_sync(h->stream, b, h->b, sizeof(double) * (size_t)h->nf_local, cudaMemcpyDefault));
   return FVB_OK;
 }
 int fvb_get_diag(fvb_handle h, double *d) {
   FVB_TRY(check_handle(h, true));
-  FVB_CUDA(cudaMemcpy(d, h->diag, sizeof(double) * (size_t)h->nf_local, cudaMemcpyDefault));
+  FVB_CUDA(memcpy_sync(h->stream, d, h->diag, sizeof(double) * (size_t)h->nf_local, cudaMemcpyDefault));
   return FVB_OK;
 }
 
@@ -751,16 +784,16 @@ static int export_nodemap(fvb_handle h, uint8_t *freenode, int64_t *n2f) {
   const int64_t n = h->n_own_nodes;
   uint8_t *d_f = nullptr;
   int64_t *d_m = nullptr;
-  if (freenode) FVB_TRY(dalloc(&d_f, n));
-  if (n2f) FVB_TRY(dalloc(&d_m, n));
+  if (freenode) FVB_TRY(dalloc(h, &d_f, n));
+  if (n2f) FVB_TRY(dalloc(h, &d_m, n));
   if (n) {
     k_export_nodemap<<<grid_for(n), kBlock, 0, h->stream>>>(h->nodemap, n, h->row_start, d_f, d_m);
     h->tm.kernel_launches++;
   }
   cudaError_t e = cudaStreamSynchronize(h->stream);
-  if (e == cudaSuccess && freenode) e = cudaMemcpy(freenode, d_f, (size_t)n, cudaMemcpyDefault);
-  if (e == cudaSuccess && n2f) e = cudaMemcpy(n2f, d_m, sizeof(int64_t) * (size_t)n, cudaMemcpyDefault);
-  dfree(d_f); dfree(d_m);
+  if (e == cudaSuccess && freenode) e = memcpy_sync(h->stream, freenode, d_f, (size_t)n, cudaMemcpyDefault);
+  if (e == cudaSuccess && n2f) e = memcpy_sync(h->stream, n2f, d_m, sizeof(int64_t) * (size_t)n, cudaMemcpyDefault);
+  dfree(h, d_f); dfree(h, d_m);
   if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
   return FVB_OK;
 }
@@ -786,10 +819,10 @@ int fvb_set_halo_plan(fvb_handle h, int n_peers, const int32_t *peer_ranks, cons
   h->peers.assign(peer_ranks, peer_ranks + n_peers);
   h->send_counts.assign(send_counts, send_counts + n_peers);
   h->recv_counts.assign(recv_counts, recv_counts + n_peers);
-  dfree(h->send_rows); dfree(h->sendbuf);
-  FVB_TRY(dalloc(&h->send_rows, ns));
-  FVB_TRY(dalloc(&h->sendbuf, ns));
-  FVB_CUDA(cudaMemcpy(h->send_rows, rows.data(), sizeof(int32_t) * (size_t)ns, cudaMemcpyHostToDevice));
+  dfree(h, h->send_rows); dfree(h, h->sendbuf);
+  FVB_TRY(dalloc(h, &h->send_rows, ns));
+  FVB_TRY(dalloc(h, &h->sendbuf, ns));
+  FVB_CUDA(memcpy_sync(h->stream, h->send_rows, rows.data(), sizeof(int32_t) * (size_t)ns, cudaMemcpyHostToDevice));
   h->n_send = ns;
   h->halo_ready = true;
   return FVB_OK;
@@ -812,14 +845,14 @@ int fvb_solve(fvb_handle h, double rtol, int64_t maxiter, const double *x0_free,
   FVB_CUDA(cudaEventRecord(h->ev[4], st));
   if (head_nodes) {
     double *d_head = nullptr;
-    FVB_TRY(dalloc(&d_head, h->n_own_nodes));
+    FVB_TRY(dalloc(h, &d_head, h->n_own_nodes));
     if (h->n_own_nodes) {
       k_scatter_heads<<<grid_for(h->n_own_nodes), kBlock, 0, st>>>(h->nodemap, h->n_own_nodes, h->x, h->dheads, d_head);
       h->tm.kernel_launches++;
     }
     cudaError_t e = cudaMemcpyAsync(head_nodes, d_head, sizeof(double) * (size_t)h->n_own_nodes, cudaMemcpyDefault, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    dfree(d_head);
+    dfree(h, d_head);
     if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
   }
   if (x_free) FVB_CUDA(cudaMemcpyAsync(x_free, h->x, sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
@@ -842,7 +875,7 @@ int fvb_spmv(fvb_handle h, double alpha, const double *x, double beta, double *y
   FVB_TRY(ensure_workspace(h));
   cudaStream_t st = h->stream;
   const int64_t n = h->nf_local;
-  if (!h->yio) FVB_TRY(dalloc(&h->yio, n));
+  if (!h->yio) FVB_TRY(dalloc(h, &h->yio, n));
   FVB_CUDA(cudaMemcpyAsync(h->u, x, sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
   if (beta != 0.0) FVB_CUDA(cudaMemcpyAsync(h->yio, y, sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
   FVB_TRY(launch_spmv(h, h->u, h->c, 0.0, false));
@@ -900,15 +933,15 @@ int fvb_vec_diffnorm(fvb_handle h, int a, int b, double *out) {
 }
 int fvb_set_storage(fvb_handle h, double Ss, const double *volumes) {
   FVB_TRY(check_handle(h, true));
-  if (!volumes) { dfree(h->Dvec); return FVB_OK; }
+  if (!volumes) { dfree(h, h->Dvec); return FVB_OK; }
   double *d_vol = nullptr;
-  FVB_TRY(dalloc(&d_vol, h->n_own_nodes));
-  if (!h->Dvec) FVB_TRY(dalloc(&h->Dvec, h->nf_local));
+  FVB_TRY(dalloc(h, &d_vol, h->n_own_nodes));
+  if (!h->Dvec) FVB_TRY(dalloc(h, &h->Dvec, h->nf_local));
   cudaMemcpyAsync(d_vol, volumes, sizeof(double) * (size_t)h->n_own_nodes, cudaMemcpyDefault, h->stream);
   k_make_D<<<vgrid(h, h->nf_local), kBlock, 0, h->stream>>>(h->nf_local, h->row2node, d_vol, Ss, h->Dvec);
   h->tm.kernel_launches++;
   cudaError_t e = cudaStreamSynchronize(h->stream);
-  dfree(d_vol);
+  dfree(h, d_vol);
   if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
   return FVB_OK;
 }
@@ -946,7 +979,7 @@ int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes) {
   FVB_TRY(check_handle(h, true));
   FVB_TRY(ensure_slot(h, slot));
   double *d_head = nullptr;
-  FVB_TRY(dalloc(&d_head, h->n_own_nodes));
+  FVB_TRY(dalloc(h, &d_head, h->n_own_nodes));
   if (h->n_own_nodes) {
     k_scatter_heads<<<grid_for(h->n_own_nodes), kBlock, 0, h->stream>>>(h->nodemap, h->n_own_nodes, h->slots[slot],
                                                                         h->dheads, d_head);
@@ -954,7 +987,7 @@ int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes) {
   }
   cudaError_t e = cudaMemcpyAsync(head_nodes, d_head, sizeof(double) * (size_t)h->n_own_nodes, cudaMemcpyDefault, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  dfree(d_head);
+  dfree(h, d_head);
   if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
   return FVB_OK;
 }
