@@ -194,6 +194,17 @@ class System:
         rc = i64(recv_counts)
         check(lib().fvb_set_halo_plan(self._h, C.c_int(pr.size), ptr(pr), ptr(sc), ptr(sr), ptr(rc)))
 
+    def peer_export(self) -> bytes:
+        buf = (C.c_uint8 * _lib.PEER_BLOB_BYTES)()
+        check(lib().fvb_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def peer_import(self, blobs_by_rank, send_dst_index):
+        raw = b"".join(blobs_by_rank)
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        dst = i64(send_dst_index)
+        check(lib().fvb_peer_import(self._h, buf, ptr(dst)))
+
     # ---- solve ---------------------------------------------------------------------------
     def solve(self, rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER, x0=None, want_head=True, want_x=False, hist_cap=None,
               head_out=None):

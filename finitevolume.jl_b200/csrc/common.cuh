@@ -41,7 +41,8 @@ struct PcgScal {
   int done, converged;
 };
 
-struct Comm;  // nccl_dyn.h
+struct Comm;      // nccl_dyn.h
+struct PeerState; // fvb200.cu (peer.cuh tables)
 
 }  // namespace fvb
 
@@ -100,6 +101,8 @@ struct fvb_handle_s {
   double *sendbuf = nullptr;
   int64_t n_send = 0;
   bool halo_ready = false;
+  fvb::PeerState *peer = nullptr;  // NVLink peer-memory exchange state (null: NCCL path)
+  int64_t u_cap = 0;               // capacity of u (plain cudaMalloc when nranks > 1: IPC-exportable)
 
   // index-free diagonal copy of A (dia.cuh), built when the pattern allows
   int fmt_request = 0;          // 0 auto, 1 CSR only

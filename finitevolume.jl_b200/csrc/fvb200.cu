@@ -14,6 +14,7 @@
 #include "dia.cuh"
 #include "nccl_dyn.h"
 #include "pcg.cuh"
+#include "peer.cuh"
 #include "scan.cuh"
 #include "spmv.cuh"
 
@@ -23,6 +24,19 @@ int set_error(int code, const std::string &msg) {
   g_last_error = msg;
   return code;
 }
+}  // namespace fvb
+
+namespace fvb {
+struct PeerState {
+  bool active = false;
+  PeerMail *mail = nullptr;             // this rank's mailbox (cudaMalloc, exported)
+  void *opened_u[kMaxRanks] = {};       // cudaIpcOpenMemHandle results (to close)
+  void *opened_mail[kMaxRanks] = {};
+  PeerTable tab = {};
+  HaloPlanDev push = {}, wait = {};
+  unsigned long long red_seq = 0, halo_seq = 0;
+  std::vector<uint8_t> last_blobs;      // what the open mappings correspond to
+};
 }  // namespace fvb
 
 using namespace fvb;
@@ -70,7 +84,9 @@ void free_problem(fvb_handle h) {
   dfree(h, h->nodemap); dfree(h, h->row2node); dfree(h, h->sources); dfree(h, h->dheads); dfree(h, h->aol);
   dfree(h, h->meta); dfree(h, h->cface); dfree(h, h->adjptr); dfree(h, h->adj_face); dfree(h, h->adj_col);
   dfree(h, h->halo_glob); dfree(h, h->rowptr); dfree(h, h->colidx); dfree(h, h->vals); dfree(h, h->b); dfree(h, h->diag);
-  dfree(h, h->x); dfree(h, h->r); dfree(h, h->u); dfree(h, h->c); dfree(h, h->dinv); dfree(h, h->rhs); dfree(h, h->Dvec);
+  dfree(h, h->x); dfree(h, h->r); dfree(h, h->c); dfree(h, h->dinv); dfree(h, h->rhs); dfree(h, h->Dvec);
+  if (h->nranks == 1) { dfree(h, h->u); h->u_cap = 0; }  // multi-rank: u is IPC-exported, kept and reused
+  if (h->peer) h->peer->active = false;                  // plan changes: peers must be re-imported
   for (auto &s : h->slots) dfree(h, s);
   dfree(h, h->partials); dfree(h, h->hist); dfree(h, h->xio); dfree(h, h->yio);
   dfree(h, h->send_rows); dfree(h, h->sendbuf);
@@ -97,7 +113,15 @@ int ensure_workspace(fvb_handle h) {
   const int64_t n = h->nf_local;
   if (!h->x) {
     FVB_TRY(dalloc(h, &h->x, n)); FVB_TRY(dalloc(h, &h->r, n)); FVB_TRY(dalloc(h, &h->c, n));
-    FVB_TRY(dalloc(h, &h->u, n + h->n_halo)); FVB_TRY(dalloc(h, &h->dinv, n)); FVB_TRY(dalloc(h, &h->rhs, n));
+    FVB_TRY(dalloc(h, &h->dinv, n)); FVB_TRY(dalloc(h, &h->rhs, n));
+    if (h->nranks == 1) {
+      FVB_TRY(dalloc(h, &h->u, n + h->n_halo));
+    } else if (h->u_cap < n + h->n_halo) {
+      if (h->u) FVB_CUDA(cudaFree(h->u));
+      h->u = nullptr;
+      h->u_cap = std::max<int64_t>(n + h->n_halo, 1);
+      FVB_CUDA(cudaMalloc((void **)&h->u, sizeof(double) * (size_t)h->u_cap));
+    }
     FVB_TRY(dalloc(h, &h->partials, 2 * (int64_t)std::max(cdiv(n, kSpmvRows), h->num_sms * 8) + 2));
     FVB_CUDA(cudaMemsetAsync(h->u, 0, sizeof(double) * (size_t)std::max<int64_t>(n + h->n_halo, 1), h->stream));
   }
@@ -118,6 +142,21 @@ int ensure_hist(fvb_handle h, int64_t cap) {
 int halo_exchange(fvb_handle h, double *vec) {
   if (h->nranks == 1) return FVB_OK;
   if (!h->halo_ready) return set_error(FVB_ERR_STATE, "fvb_set_halo_plan has not been called on this rank");
+  if (h->peer && h->peer->active && vec == h->u) {
+    // NVLink peer stores + flags (peer.cuh)
+    PeerState &P = *h->peer;
+    const unsigned long long seq = ++P.halo_seq;
+    if (P.push.npeers > 0) {
+      const int g = std::max(1, std::min(cdiv(h->n_send, kBlock), h->num_sms * 2));
+      k_halo_push<<<g, kBlock, 0, h->stream>>>(P.tab, P.push, h->send_rows, vec, seq, h->ticket + 1);
+      h->tm.kernel_launches++;
+    }
+    if (P.wait.npeers > 0) {
+      k_halo_wait<<<1, 32, 0, h->stream>>>(P.mail, P.wait, seq, h->scal);
+      h->tm.kernel_launches++;
+    }
+    return FVB_OK;
+  }
   if (h->n_send > 0) {
     k_pack<<<grid_for(h->n_send), kBlock, 0, h->stream>>>(h->n_send, h->send_rows, vec, h->sendbuf);
     h->tm.kernel_launches++;
@@ -137,9 +176,21 @@ int halo_exchange(fvb_handle h, double *vec) {
   return FVB_OK;
 }
 
-int allreduce_sum(fvb_handle h, double *dev, int count) {
+// Sum scal->red[0..count) over the ranks and advance the recurrence (mode: FIN_*).
+int allreduce_fin(fvb_handle h, int count, int mode) {
   if (h->nranks == 1) return FVB_OK;
-  FVB_NCCL(nccl().AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, h->comm->comm, h->stream));
+  double *red = h->scal->red;
+  if (h->peer && h->peer->active) {
+    PeerState &P = *h->peer;
+    k_allreduce_fin<<<1, 32, 0, h->stream>>>(P.tab, ++P.red_seq, red, count, mode, h->scal, h->hist);
+    h->tm.kernel_launches++;
+    return FVB_OK;
+  }
+  FVB_NCCL(nccl().AllReduce(red, red, (size_t)count, ncclDouble, ncclSum, h->comm->comm, h->stream));
+  if (mode == FIN_INIT) k_fin_init<<<1, 1, 0, h->stream>>>(h->scal);
+  else if (mode == FIN_UC) k_fin_uc<<<1, 1, 0, h->stream>>>(h->scal);
+  else if (mode == FIN_ITER) k_fin_iter<<<1, 1, 0, h->stream>>>(h->scal, h->hist);
+  if (mode != FIN_NONE) h->tm.kernel_launches++;
   return FVB_OK;
 }
 
@@ -287,11 +338,7 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
   k_pcg_init<<<vg, kBlock, 0, st>>>(n, rhs, h->c, have_x0 ? 1 : 0, h->dinv, h->x, h->r, h->partials, h->ticket,
                                     h->scal, fin);
   h->tm.kernel_launches++;
-  if (!fin) {
-    FVB_TRY(allreduce_sum(h, h->scal->red, 2));
-    k_fin_init<<<1, 1, 0, st>>>(h->scal);
-    h->tm.kernel_launches++;
-  }
+  if (!fin) FVB_TRY(allreduce_fin(h, 2, FIN_INIT));
   // Enqueue iterations in batches; poll the device scalars one batch behind so the GPU
   // never waits for the host.
   int64_t enq = 0;
@@ -304,19 +351,11 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
       k_update_u<<<vg, kBlock, 0, st>>>(n, h->dinv, h->r, h->u, h->scal);
       h->tm.kernel_launches++;
       FVB_TRY(launch_spmv(h, h->u, h->c, sigma, true));
-      if (!fin) {
-        FVB_TRY(allreduce_sum(h, h->scal->red, 1));
-        k_fin_uc<<<1, 1, 0, st>>>(h->scal);
-        h->tm.kernel_launches++;
-      }
+      if (!fin) FVB_TRY(allreduce_fin(h, 1, FIN_UC));
       k_update_xr<<<vg, kBlock, 0, st>>>(n, h->u, h->c, h->dinv, h->x, h->r, h->partials, h->ticket, h->scal,
                                          h->hist, fin);
       h->tm.kernel_launches++;
-      if (!fin) {
-        FVB_TRY(allreduce_sum(h, h->scal->red, 2));
-        k_fin_iter<<<1, 1, 0, st>>>(h->scal, h->hist);
-        h->tm.kernel_launches++;
-      }
+      if (!fin) FVB_TRY(allreduce_fin(h, 2, FIN_ITER));
     }
     enq += todo;
     FVB_CUDA(cudaMemcpyAsync(&h->scal_host[slot], h->scal, sizeof(PcgScal), cudaMemcpyDeviceToHost, st));
@@ -334,6 +373,11 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
   FVB_CUDA(memcpy_sync(h->stream, &h->scal_host[0], h->scal, sizeof(PcgScal), cudaMemcpyDeviceToHost));
   if (iters) *iters = h->scal_host[0].iter;
   if (converged) *converged = h->scal_host[0].converged;
+  if (h->peer && h->peer->active) {
+    int perr = 0;
+    FVB_CUDA(memcpy_sync(st, &perr, &h->peer->mail->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (perr) return set_error(FVB_ERR_NCCL, "peer-memory exchange timed out waiting for another rank");
+  }
   h->tm.spmv_ms_total = 0;
   h->tm.spmv_samples = 0;
   for (int k = 0; k < h->prof_count; ++k) {
@@ -409,6 +453,15 @@ int fvb_destroy(fvb_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   free_problem(h);
+  if (h->peer) {
+    for (int r = 0; r < kMaxRanks; ++r) {
+      if (h->peer->opened_u[r]) cudaIpcCloseMemHandle(h->peer->opened_u[r]);
+      if (h->peer->opened_mail[r]) cudaIpcCloseMemHandle(h->peer->opened_mail[r]);
+    }
+    if (h->peer->mail) cudaFree(h->peer->mail);
+    delete h->peer;
+  }
+  if (h->nranks > 1 && h->u) cudaFree(h->u);
   if (h->comm) {
     if (h->comm->comm) nccl().CommDestroy(h->comm->comm);
     delete h->comm;
@@ -828,6 +881,82 @@ int fvb_set_halo_plan(fvb_handle h, int n_peers, const int32_t *peer_ranks, cons
   return FVB_OK;
 }
 
+int fvb_peer_export(fvb_handle h, uint8_t blob[FVB_PEER_BLOB_BYTES]) {
+  static_assert(2 * sizeof(cudaIpcMemHandle_t) == FVB_PEER_BLOB_BYTES, "blob = two IPC handles");
+  FVB_TRY(check_handle(h, true));
+  if (h->nranks < 2 || h->nranks > kMaxRanks) return set_error(FVB_ERR_STATE, "peer exchange needs 2..8 ranks (fvb_comm_init)");
+  FVB_TRY(ensure_workspace(h));
+  if (!h->peer) h->peer = new PeerState();
+  PeerState &P = *h->peer;
+  P.active = false;
+  if (!P.mail) {
+    FVB_CUDA(cudaMalloc((void **)&P.mail, sizeof(PeerMail)));
+    FVB_CUDA(cudaMemsetAsync(P.mail, 0, sizeof(PeerMail), h->stream));
+  }
+  FVB_CUDA(cudaStreamSynchronize(h->stream));
+  cudaIpcMemHandle_t hu, hm;
+  FVB_CUDA(cudaIpcGetMemHandle(&hu, h->u));
+  FVB_CUDA(cudaIpcGetMemHandle(&hm, P.mail));
+  memcpy(blob, &hu, sizeof(hu));
+  memcpy(blob + sizeof(hu), &hm, sizeof(hm));
+  return FVB_OK;
+}
+
+int fvb_peer_import(fvb_handle h, const uint8_t *blobs, const int64_t *send_dst_index) {
+  FVB_TRY(check_handle(h, true));
+  if (!h->peer || !h->peer->mail) return set_error(FVB_ERR_STATE, "call fvb_peer_export first");
+  if (!h->halo_ready) return set_error(FVB_ERR_STATE, "call fvb_set_halo_plan first");
+  PeerState &P = *h->peer;
+  // Re-assembly of a same-sized problem exports the very same allocations: keep the mappings
+  // (cudaIpcOpenMemHandle costs ~0.1 s per peer) and only rebuild the plan tables.
+  std::vector<uint8_t> nb(blobs, blobs + (size_t)h->nranks * FVB_PEER_BLOB_BYTES);
+  bool reuse = nb == P.last_blobs;
+  for (size_t p = 0; reuse && p < h->peers.size(); ++p) reuse = P.tab.u[h->peers[p]] != nullptr;
+  if (!reuse) {
+    for (int r = 0; r < kMaxRanks; ++r) {
+      if (P.opened_u[r]) { cudaIpcCloseMemHandle(P.opened_u[r]); P.opened_u[r] = nullptr; }
+      if (P.opened_mail[r]) { cudaIpcCloseMemHandle(P.opened_mail[r]); P.opened_mail[r] = nullptr; }
+    }
+    P.tab = PeerTable{};
+    P.last_blobs.clear();
+  }
+  P.tab.nranks = h->nranks;
+  P.tab.rank = h->rank;
+  for (int r = 0; r < h->nranks && !reuse; ++r) {
+    if (r == h->rank) { P.tab.u[r] = h->u; P.tab.mail[r] = P.mail; continue; }
+    cudaIpcMemHandle_t hu, hm;
+    memcpy(&hu, blobs + (size_t)r * FVB_PEER_BLOB_BYTES, sizeof(hu));
+    memcpy(&hm, blobs + (size_t)r * FVB_PEER_BLOB_BYTES + sizeof(hu), sizeof(hm));
+    // only neighbours' vectors are written; every rank's mailbox is
+    bool is_peer = std::find(h->peers.begin(), h->peers.end(), r) != h->peers.end();
+    if (is_peer) {
+      FVB_CUDA(cudaIpcOpenMemHandle(&P.opened_u[r], hu, cudaIpcMemLazyEnablePeerAccess));
+      P.tab.u[r] = (double *)P.opened_u[r];
+    }
+    FVB_CUDA(cudaIpcOpenMemHandle(&P.opened_mail[r], hm, cudaIpcMemLazyEnablePeerAccess));
+    P.tab.mail[r] = (PeerMail *)P.opened_mail[r];
+  }
+  P.last_blobs = nb;
+  P.push = HaloPlanDev{};
+  P.wait = HaloPlanDev{};
+  long long so = 0;
+  for (size_t p = 0; p < h->peers.size(); ++p) {
+    if (h->send_counts[p] > 0) {
+      const int k = P.push.npeers++;
+      P.push.peer[k] = h->peers[p];
+      P.push.send_begin[k] = so;
+      P.push.dst_off[k] = send_dst_index[p];
+      P.push.send_begin[k + 1] = so + h->send_counts[p];
+    }
+    so += h->send_counts[p];
+    if (h->recv_counts[p] > 0) P.wait.peer[P.wait.npeers++] = h->peers[p];
+  }
+  // send_rows is laid out peer after peer in plan order; push.send_begin indexes it directly
+  // only if peers without sends contribute nothing, which holds because their count is 0.
+  P.active = true;
+  return FVB_OK;
+}
+
 int fvb_solve(fvb_handle h, double rtol, int64_t maxiter, const double *x0_free, double *head_nodes, double *x_free,
               int64_t *iters, int *converged, double *resnorm_hist, int64_t hist_cap) {
   FVB_TRY(check_handle(h, true));
@@ -924,7 +1053,7 @@ int fvb_vec_diffnorm(fvb_handle h, int a, int b, double *out) {
   const int64_t n = h->nf_local;
   k_diffnorm2<<<vgrid(h, n), kBlock, 0, h->stream>>>(n, h->slots[a], h->slots[b], h->partials, h->ticket, h->scal->red);
   h->tm.kernel_launches++;
-  FVB_TRY(allreduce_sum(h, h->scal->red, 1));
+  FVB_TRY(allreduce_fin(h, 1, FIN_NONE));
   double s = 0;
   FVB_CUDA(cudaMemcpyAsync(&s, h->scal->red, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   FVB_CUDA(cudaStreamSynchronize(h->stream));

@@ -74,8 +74,21 @@ def halo_plan_from_ranges(rank, row_ranges, halo_cols_by_rank):
     return peers, send_counts, send_rows, recv_counts
 
 
-def exchange_halo_plan(system, group=None):
-    """Collective: gather row ranges and halo lists over torch.distributed and install the plan."""
+def send_destinations(rank, peers, row_ranges, halo_cols_by_rank):
+    """For each peer of `rank`'s plan: the index in the PEER's vector where this rank's first halo
+    value belongs = peer's nf_local + number of the peer's halo columns owned by lower ranks
+    (halo columns ascend, ranks own ascending row ranges)."""
+    my_start = row_ranges[rank][0]
+    return [int(row_ranges[p][1] + np.searchsorted(np.asarray(halo_cols_by_rank[p], np.int64), my_start))
+            for p in peers]
+
+
+def exchange_halo_plan(system, group=None, peer_memory=None):
+    """Collective: gather row ranges and halo lists over torch.distributed and install the plan.
+    peer_memory (default: on unless FVB_P2P=0): also map the neighbours' vectors and mailboxes
+    through CUDA IPC so the per-iteration exchanges run over NVLink peer memory instead of NCCL."""
+    import os
+
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -83,8 +96,16 @@ def exchange_halo_plan(system, group=None):
     mine = (int(s["row_start"]), int(s["nf_local"]), system.halo_cols())
     gathered = [None] * world
     dist.all_gather_object(gathered, mine, group=group)
-    plan = halo_plan_from_ranges(rank, [(g[0], g[1]) for g in gathered], [g[2] for g in gathered])
+    ranges = [(g[0], g[1]) for g in gathered]
+    halos = [g[2] for g in gathered]
+    plan = halo_plan_from_ranges(rank, ranges, halos)
     system.set_halo_plan(*plan)
+    if peer_memory is None:
+        peer_memory = os.environ.get("FVB_P2P", "1") != "0"
+    if peer_memory and world > 1 and hasattr(system, "peer_export"):
+        blobs = [None] * world
+        dist.all_gather_object(blobs, system.peer_export(), group=group)
+        system.peer_import(blobs, send_destinations(rank, plan[0], ranges, halos))
     return plan
 
 

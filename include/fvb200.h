@@ -119,6 +119,18 @@ int fvb_set_halo_plan(fvb_handle h, int n_peers, const int32_t *peer_ranks,
                       const int64_t *send_counts, const int32_t *send_rows,
                       const int64_t *recv_counts);
 
+/* ---- NVLink peer-memory exchange (optional, same node, after fvb_set_halo_plan) --------------
+ * Replaces the per-iteration NCCL calls (halo send/recv, two all-reduces) by kernels that store
+ * straight into the neighbours' memory mapped through CUDA IPC.  Every rank calls
+ * fvb_peer_export, the 128-byte blobs are all-gathered by the host harness, then every rank
+ * calls fvb_peer_import with the blobs in rank order and, per peer of its halo plan, the index
+ * in that peer's vector where this rank's first halo value belongs
+ * (= peer's nf_local + number of the peer's halo columns owned by lower ranks).
+ * Without these calls the NCCL path is used. */
+#define FVB_PEER_BLOB_BYTES 128
+int fvb_peer_export(fvb_handle h, uint8_t blob[FVB_PEER_BLOB_BYTES]);
+int fvb_peer_import(fvb_handle h, const uint8_t *blobs_by_rank, const int64_t *send_dst_index);
+
 /* ---- steady solve: the cg call of solvediffusion (src/FiniteVolume.jl:160-161) with
  * Pl = Jacobi instead of Ruge-Stueben AMG (north_star), followed by freenodes2nodes
  * (:141-155).  Stopping rule of IterativeSolvers.cg 0.8.1: ||r|| <= rtol * ||r0||.

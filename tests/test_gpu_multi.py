@@ -15,11 +15,13 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"])
 @pytest.mark.parametrize("world,ns", [(2, "20,12,10"), (2, "7,9,5"), (4, "23,8,6"), (8, "40,6,6")])
-def test_slab_solve_over_nccl(fv, world, ns):
+def test_slab_solve_multi_gpu(fv, world, ns, p2p):
+    """p2p=1: halo planes and CG scalars over NVLink peer memory (CUDA IPC); p2p=0: NCCL."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    env = dict(os.environ, FV_NS=ns)
+    env = dict(os.environ, FV_NS=ns, FVB_P2P=p2p)
     port = 29600 + (os.getpid() + world) % 300
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")]
