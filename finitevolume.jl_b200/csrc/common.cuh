@@ -36,6 +36,7 @@ inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // host every few iterations through pinned memory.
 struct PcgScal {
   double rho, rho_prev, uc, resid, resid0, reltol, tol;
+  double alpha_prev;   // step length of the last closed iteration; its x += alpha*u is applied lazily
   double red[4];       // local partial sums awaiting the (optional) all-reduce
   long long iter, maxiter, hist_cap;
   int done, converged;

@@ -348,12 +348,11 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
   while (!stop) {
     int64_t todo = std::min<int64_t>(batch, maxiter - enq);
     for (int64_t it = 0; it < todo; ++it) {
-      k_update_u<<<vg, kBlock, 0, st>>>(n, h->dinv, h->r, h->u, h->scal);
+      k_update_u<<<vg, kBlock, 0, st>>>(n, h->dinv, h->r, h->u, h->x, h->scal);
       h->tm.kernel_launches++;
       FVB_TRY(launch_spmv(h, h->u, h->c, sigma, true));
       if (!fin) FVB_TRY(allreduce_fin(h, 1, FIN_UC));
-      k_update_xr<<<vg, kBlock, 0, st>>>(n, h->u, h->c, h->dinv, h->x, h->r, h->partials, h->ticket, h->scal,
-                                         h->hist, fin);
+      k_update_xr<<<vg, kBlock, 0, st>>>(n, h->c, h->dinv, h->r, h->partials, h->ticket, h->scal, h->hist, fin);
       h->tm.kernel_launches++;
       if (!fin) FVB_TRY(allreduce_fin(h, 2, FIN_ITER));
     }
@@ -369,6 +368,8 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
     if (enq >= maxiter) stop = true;
     if (batch < 64) batch *= 2;
   }
+  k_finish_x<<<vg, kBlock, 0, st>>>(n, h->u, h->x, h->scal);
+  h->tm.kernel_launches++;
   FVB_CUDA(cudaStreamSynchronize(st));
   FVB_CUDA(memcpy_sync(h->stream, &h->scal_host[0], h->scal, sizeof(PcgScal), cudaMemcpyDeviceToHost));
   if (iters) *iters = h->scal_host[0].iter;

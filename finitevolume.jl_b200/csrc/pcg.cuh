@@ -5,7 +5,9 @@
 //     c = Pl \ r ; rho_prev = rho ; rho = c.r ; beta = rho/rho_prev ; u = c + beta u
 //     c = A u ; alpha = rho / u.c ; x += alpha u ; r -= alpha c ; residual = ||r||
 //     stop when residual <= tol * ||r0|| or iteration == maxiter
-// One iteration = three launches: k_update_u, k_spmv<DOT>, k_update_xr.  All scalars stay
+// One iteration = three launches: k_update_u, k_spmv<DOT>, k_update_xr.  The update x += alpha u
+// of iteration k is deferred into k_update_u of iteration k+1, where u is read anyway (saves one
+// pass over u per iteration); k_finish_x applies the last one after the loop.  All scalars stay
 // in device memory (PcgScal); every kernel returns at once when scal->done is set, so the
 // host can enqueue iterations in batches without synchronising.
 #pragma once
@@ -26,6 +28,7 @@ __device__ __forceinline__ void pcg_finish_init(PcgScal *s, double rho0, double 
 }
 
 __device__ __forceinline__ void pcg_finish_iter(PcgScal *s, double rho_new, double rr, double *hist) {
+  s->alpha_prev = s->rho / s->uc;
   s->rho_prev = s->rho;
   s->rho = rho_new;
   const double resid = sqrt(rr);
@@ -43,7 +46,7 @@ __global__ void k_fin_iter(PcgScal *s, double *hist) { if (!s->done) pcg_finish_
 
 __global__ void k_set_scal(PcgScal *s, double tol, long long maxiter, long long hist_cap) {
   s->tol = tol; s->maxiter = maxiter; s->hist_cap = hist_cap;
-  s->done = 0; s->converged = 0; s->iter = 0;
+  s->done = 0; s->converged = 0; s->iter = 0; s->alpha_prev = 0.0;
   s->rho = 0; s->rho_prev = 1; s->uc = 0; s->resid = 0; s->resid0 = 0; s->reltol = 0;
 }
 
@@ -77,26 +80,34 @@ k_pcg_init(int64_t n, const double *__restrict__ rhs, const double *__restrict__
   }
 }
 
-// u = dinv .* r + beta * u
+// x += alpha_prev * u (the deferred update of the previous iteration); u = dinv .* r + beta * u
 __global__ void __launch_bounds__(kBlock)
 k_update_u(int64_t n, const double *__restrict__ dinv, const double *__restrict__ r, double *__restrict__ u,
-           const PcgScal *__restrict__ scal) {
+           double *__restrict__ x, const PcgScal *__restrict__ scal) {
   if (scal->done) return;
-  const double beta = scal->iter == 0 ? 0.0 : scal->rho / scal->rho_prev;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    u[i] = dinv[i] * r[i] + beta * u[i];
+  const bool first = scal->iter == 0;
+  const double beta = first ? 0.0 : scal->rho / scal->rho_prev;
+  const double ap = scal->alpha_prev;
+  if (first) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      u[i] = dinv[i] * r[i];
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const double ui = u[i];
+      x[i] += ap * ui;
+      u[i] = dinv[i] * r[i] + beta * ui;
+    }
+  }
 }
 
-// x += alpha u ; r -= alpha c ; sums (dinv r).r and r.r ; last block closes the iteration
+// r -= alpha c ; sums (dinv r).r and r.r ; last block closes the iteration
 __global__ void __launch_bounds__(kBlock)
-k_update_xr(int64_t n, const double *__restrict__ u, const double *__restrict__ c,
-            const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r,
+k_update_xr(int64_t n, const double *__restrict__ c, const double *__restrict__ dinv, double *__restrict__ r,
             double *partials, unsigned int *ticket, PcgScal *scal, double *hist, int finalize_mode) {
   if (scal->done) return;
   const double alpha = scal->rho / scal->uc;
   double s0 = 0.0, s1 = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    x[i] += alpha * u[i];
     const double ri = r[i] - alpha * c[i];
     r[i] = ri;
     s0 += dinv[i] * ri * ri;
@@ -109,6 +120,15 @@ k_update_xr(int64_t n, const double *__restrict__ u, const double *__restrict__ 
     scal->red[0] = t0; scal->red[1] = t1;
     if (finalize_mode == 1) pcg_finish_iter(scal, t0, t1, hist);
   }
+}
+
+// after the loop: the x update of the last closed iteration (alpha_prev = 0 if none)
+__global__ void __launch_bounds__(kBlock)
+k_finish_x(int64_t n, const double *__restrict__ u, double *__restrict__ x, PcgScal *scal) {
+  const double ap = scal->alpha_prev;
+  if (ap == 0.0) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] += ap * u[i];
 }
 
 // ---- small vector helpers for the transient path (src/transient.jl:71, :81) ---------------
