@@ -272,6 +272,17 @@ class System:
         check(lib().fvb_time_spmv(self._h, C.c_int(warmup), C.c_int(reps), C.byref(out)))
         return out.value
 
+    def set_preconditioner(self, kind="jacobi", nu=0, omega=0.0, oc=0.0):
+        """"jacobi" (north_star default) or "mg" (aggregation multigrid V-cycle; box-structured
+        matrices only -- raises FVBError otherwise when called after assemble)."""
+        k = {"jacobi": 0, "mg": 1}[kind]
+        check(lib().fvb_set_preconditioner(self._h, C.c_int(k), C.c_int(int(nu)), C.c_double(omega), C.c_double(oc)))
+
+    def preconditioner(self):
+        a, l = C.c_int(), C.c_int()
+        check(lib().fvb_get_preconditioner(self._h, C.byref(a), C.byref(l)))
+        return ("mg" if a.value == 1 else "jacobi"), l.value
+
     def set_spmv_format(self, fmt):
         """0 = automatic (diagonal copy when the pattern allows), 1 = always CSR."""
         check(lib().fvb_set_spmv_format(self._h, C.c_int(int(fmt))))
@@ -381,13 +392,21 @@ def freenodes2nodes(result, sources, dirichletnodes, dirichletheads, device=0):
 
 
 def solvediffusion(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
-                   maxiter=DEFAULT_MAXITER, rtol=SQRT_EPS, metaindex=None, logtransformconductivity=False, device=0):
+                   maxiter=DEFAULT_MAXITER, rtol=SQRT_EPS, metaindex=None, logtransformconductivity=False, device=0,
+                   precond="jacobi"):
     """src/FiniteVolume.jl:157-165 -> (head, ch, A, b, freenode).
 
     Differences from the reference, both mandated by north_star: the preconditioner is
     Jacobi instead of Ruge-Stueben AMG, so `maxiter` counts Jacobi-PCG iterations (default
-    raised from 400 accordingly); `rtol` exposes IterativeSolvers' `tol` (same default)."""
-    s = System(device).assemble(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
-                                metaindex, logtransformconductivity)
+    raised from 400 accordingly); `rtol` exposes IterativeSolvers' `tol` (same default).
+    precond="mg" selects the aggregation-multigrid V-cycle (box-structured grids),
+    "auto" uses it when the matrix qualifies and Jacobi otherwise."""
+    s = System(device)
+    if precond in ("mg", "auto"):
+        s.set_preconditioner("mg")  # before assemble: silently stays on Jacobi when the matrix does not qualify
+    s.assemble(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
+               metaindex, logtransformconductivity)
+    if precond == "mg" and s.preconditioner()[0] != "mg":
+        raise _lib.FVBError(1, "multigrid needs a box-structured 7-point matrix; use precond='auto' or 'jacobi'")
     head, _, ch = s.solve(rtol=rtol, maxiter=maxiter)
     return head, ch, SparseMatrixCSC(s), s.b(), s.freenode()

@@ -44,6 +44,7 @@ struct PcgScal {
 
 struct Comm;      // nccl_dyn.h
 struct PeerState; // fvb200.cu (peer.cuh tables)
+struct MgState;   // fvb200.cu (mg.cuh hierarchy)
 
 }  // namespace fvb
 
@@ -112,6 +113,12 @@ struct fvb_handle_s {
   int64_t dia_off[4] = {};
   double *dia_U[4] = {};
   int64_t dia_lo0 = 0, dia_nlo = 0, dia_hi0 = 0, dia_nhi = 0;
+
+  // preconditioner: 0 Jacobi, 1 aggregation multigrid (mg.cuh)
+  int precond_request = 0;
+  int mg_nu = 2;
+  double mg_omega = 0.8, mg_oc = 1.5;
+  fvb::MgState *mg = nullptr;
 
   // in-situ SpMV launch timing (fvb_set_profiling)
   int prof_stride = 0;

@@ -37,6 +37,12 @@ struct PeerState {
   unsigned long long red_seq = 0, halo_seq = 0;
   std::vector<uint8_t> last_blobs;      // what the open mappings correspond to
 };
+struct MgState {
+  bool ready = false;
+  int nlev = 0;
+  MgLevel lev[kMgMaxLevels];
+  double *own[kMgMaxLevels][7] = {};  // diag, up0..2, x, r, t owned by level l (level 0 owns only x, t)
+};
 }  // namespace fvb
 
 using namespace fvb;
@@ -93,6 +99,11 @@ void free_problem(fvb_handle h) {
   for (auto &u : h->dia_U) dfree(h, u);
   h->dia_on = false;
   h->dia_K = 0;
+  if (h->mg) {
+    for (auto &lv : h->mg->own) for (auto &p : lv) dfree(h, p);
+    h->mg->ready = false;
+    h->mg->nlev = 0;
+  }
   h->hist_cap = 0;
   h->assembled = false;
   h->halo_ready = false;
@@ -190,6 +201,8 @@ int allreduce_fin(fvb_handle h, int count, int mode) {
   if (mode == FIN_INIT) k_fin_init<<<1, 1, 0, h->stream>>>(h->scal);
   else if (mode == FIN_UC) k_fin_uc<<<1, 1, 0, h->stream>>>(h->scal);
   else if (mode == FIN_ITER) k_fin_iter<<<1, 1, 0, h->stream>>>(h->scal, h->hist);
+  else if (mode == FIN_RZ) k_fin_rz<<<1, 1, 0, h->stream>>>(h->scal);
+  else if (mode == FIN_R) k_fin_r<<<1, 1, 0, h->stream>>>(h->scal, h->hist);
   if (mode != FIN_NONE) h->tm.kernel_launches++;
   return FVB_OK;
 }
@@ -318,6 +331,107 @@ int build_dia(fvb_handle h, bool structure) {
   return FVB_OK;
 }
 
+// ---- aggregation multigrid (mg.cuh) ------------------------------------------------------------------------
+int mg_grid(fvb_handle h, int64_t n) { return std::max(1, std::min(cdiv(n, kBlock), h->num_sms * kMgCtasPerSm)); }
+
+// Build (structure=true) or refresh the Galerkin hierarchy from the diagonal copy of A.
+// Returns FVB_OK with mg->ready=false when the matrix does not qualify.
+int mg_setup(fvb_handle h, bool structure) {
+  cudaStream_t st = h->stream;
+  if (!h->mg) h->mg = new MgState();
+  MgState &M = *h->mg;
+  if (structure) {
+    for (auto &lv : M.own) for (auto &p : lv) dfree(h, p);
+    M.ready = false;
+    M.nlev = 0;
+    if (!h->dia_on || h->dia_K != 3 || h->dia_off[0] != 1) return FVB_OK;
+    const int64_t n = h->nf_local, nz = h->dia_off[1], nynz = h->dia_off[2];
+    if (nz < 2 || nynz % nz != 0 || n % nynz != 0 || nynz / nz < 2 || n / nynz < 1) return FVB_OK;
+    MgLevel &L0 = M.lev[0];
+    L0.nz = (int)nz; L0.ny = (int)(nynz / nz); L0.nx = (int)(n / nynz); L0.n = n;
+    L0.diag = h->diag;
+    for (int k = 0; k < 3; ++k) L0.up[k] = h->dia_U[k] + h->dia_off[k];
+    int *d_flag = nullptr;
+    FVB_TRY(dalloc(h, &d_flag, 1));
+    cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+    k_mg_check_box<<<mg_grid(h, n), kBlock, 0, st>>>(L0, d_flag);
+    h->tm.kernel_launches++;
+    int flag = 1;
+    cudaError_t e = memcpy_sync(st, &flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+    dfree(h, d_flag);
+    if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+    if (flag) return FVB_OK;
+    FVB_TRY(dalloc(h, &M.own[0][4], n));  // x (= z, the preconditioned residual)
+    FVB_TRY(dalloc(h, &M.own[0][6], n));  // t
+    L0.x = M.own[0][4]; L0.r = nullptr; L0.t = M.own[0][6];
+    int l = 0;
+    while (M.lev[l].n > kMgCoarsest && l + 1 < kMgMaxLevels) {
+      const MgLevel &F = M.lev[l];
+      MgLevel &C = M.lev[l + 1];
+      C.nx = (F.nx + 1) / 2; C.ny = (F.ny + 1) / 2; C.nz = (F.nz + 1) / 2;
+      C.n = (int64_t)C.nx * C.ny * C.nz;
+      for (int a = 0; a < 7; ++a) FVB_TRY(dalloc(h, &M.own[l + 1][a], C.n));
+      C.diag = M.own[l + 1][0];
+      for (int k = 0; k < 3; ++k) C.up[k] = M.own[l + 1][1 + k];
+      C.x = M.own[l + 1][4]; C.r = M.own[l + 1][5]; C.t = M.own[l + 1][6];
+      ++l;
+    }
+    M.nlev = l + 1;
+  }
+  if (M.nlev == 0) return FVB_OK;
+  for (int l = 0; l + 1 < M.nlev; ++l) {
+    const MgLevel &C = M.lev[l + 1];
+    k_mg_coarsen<<<grid_for(C.n), kBlock, 0, st>>>(M.lev[l], C.nx, C.ny, C.nz, M.own[l + 1][0], M.own[l + 1][1],
+                                                   M.own[l + 1][2], M.own[l + 1][3]);
+    h->tm.kernel_launches++;
+  }
+  M.ready = true;
+  return FVB_OK;
+}
+
+// z = M^-1 r : one V-cycle.  r is only read; the result lands in lev[0].x.
+void mg_vcycle(fvb_handle h, const double *r) {
+  MgState &M = *h->mg;
+  cudaStream_t st = h->stream;
+  const int nu = h->mg_nu;
+  const double om = h->mg_omega, oc = h->mg_oc;
+  M.lev[0].r = const_cast<double *>(r);
+  // going down
+  for (int l = 0; l + 1 < M.nlev; ++l) {
+    MgLevel &L = M.lev[l];
+    const int g = mg_grid(h, L.n);
+    double *cur = L.t, *oth = L.x;  // 2*nu-1 swaps in total: start in t to finish in x
+    k_mg_smooth0<<<g, kBlock, 0, st>>>(L, L.r, cur, om, h->scal);
+    for (int s = 1; s < nu; ++s) { k_mg_smooth<<<g, kBlock, 0, st>>>(L, L.r, cur, oth, om, h->scal); std::swap(cur, oth); }
+    const MgLevel &C = M.lev[l + 1];
+    k_mg_restrict<<<mg_grid(h, C.n), kBlock, 0, st>>>(L, L.r, cur, C.nx, C.ny, C.nz, C.r, h->scal);
+    h->tm.kernel_launches += nu + 1;
+  }
+  {
+    MgLevel &L = M.lev[M.nlev - 1];
+    // (with a single level the matrix is tiny and the sweeps are the whole preconditioner)
+    k_mg_coarse_solve<<<1, kBlock, 0, st>>>(L, L.r, L.x, L.t, om, kMgCoarseSweeps, h->scal);
+    h->tm.kernel_launches++;
+  }
+  // going up
+  for (int l = M.nlev - 2; l >= 0; --l) {
+    MgLevel &L = M.lev[l];
+    const int g = mg_grid(h, L.n);
+    const MgLevel &C = M.lev[l + 1];
+    // where the pre-smoothed iterate lives: t after an odd number (nu-1 even -> t, odd -> x) of swaps
+    double *cur = ((nu - 1) % 2 == 0) ? L.t : L.x;
+    double *oth = cur == L.t ? L.x : L.t;
+    k_mg_prolong<<<g, kBlock, 0, st>>>(L, C.ny, C.nz, C.x, cur, oc, h->scal);
+    for (int s = 0; s < nu; ++s) { k_mg_smooth<<<g, kBlock, 0, st>>>(L, L.r, cur, oth, om, h->scal); std::swap(cur, oth); }
+    h->tm.kernel_launches += nu + 1;
+    // cur == L.x by construction
+  }
+}
+
+// CG preconditioned by the V-cycle, steady operator only.  x0 (if any) already in h->x.
+int pcg_mg_run(fvb_handle h, const double *rhs, bool have_x0, double rtol, int64_t maxiter, int64_t *iters,
+               int *converged);
+
 // Jacobi-PCG on (A + sigma*D) x = rhs.  x0 (if any) already sits in h->x.  Result in h->x.
 int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double rtol, int64_t maxiter,
             int64_t *iters, int *converged) {
@@ -367,6 +481,81 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
     slot ^= 1;
     if (enq >= maxiter) stop = true;
     if (batch < 64) batch *= 2;
+  }
+  k_finish_x<<<vg, kBlock, 0, st>>>(n, h->u, h->x, h->scal);
+  h->tm.kernel_launches++;
+  FVB_CUDA(cudaStreamSynchronize(st));
+  FVB_CUDA(memcpy_sync(h->stream, &h->scal_host[0], h->scal, sizeof(PcgScal), cudaMemcpyDeviceToHost));
+  if (iters) *iters = h->scal_host[0].iter;
+  if (converged) *converged = h->scal_host[0].converged;
+  if (h->peer && h->peer->active) {
+    int perr = 0;
+    FVB_CUDA(memcpy_sync(st, &perr, &h->peer->mail->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (perr) return set_error(FVB_ERR_NCCL, "peer-memory exchange timed out waiting for another rank");
+  }
+  h->tm.spmv_ms_total = 0;
+  h->tm.spmv_samples = 0;
+  for (int k = 0; k < h->prof_count; ++k) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[2 * k], h->prof_ev[2 * k + 1]) == cudaSuccess) {
+      h->tm.spmv_ms_total += ms;
+      h->tm.spmv_samples++;
+    }
+  }
+  FVB_CUDA(cudaGetLastError());
+  return FVB_OK;
+}
+
+int pcg_mg_run(fvb_handle h, const double *rhs, bool have_x0, double rtol, int64_t maxiter, int64_t *iters,
+               int *converged) {
+  const int64_t n = h->nf_local;
+  cudaStream_t st = h->stream;
+  const int fin = h->nranks == 1 ? 1 : 0;
+  const int vg = vgrid(h, n);
+  MgState &M = *h->mg;
+  FVB_TRY(ensure_hist(h, maxiter));
+  h->prof_seen = 0;
+  h->prof_count = 0;
+  k_set_scal<<<1, 1, 0, st>>>(h->scal, rtol, (long long)maxiter, (long long)h->hist_cap);
+  k_make_dinv<<<vg, kBlock, 0, st>>>(n, h->diag, nullptr, 0.0, h->dinv);
+  h->tm.kernel_launches += 2;
+  if (have_x0) {
+    FVB_CUDA(cudaMemcpyAsync(h->u, h->x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    FVB_TRY(launch_spmv(h, h->u, h->c, 0.0, false));
+  }
+  k_pcg_init<<<vg, kBlock, 0, st>>>(n, rhs, h->c, have_x0 ? 1 : 0, h->dinv, h->x, h->r, h->partials, h->ticket,
+                                    h->scal, fin);
+  h->tm.kernel_launches++;
+  if (!fin) FVB_TRY(allreduce_fin(h, 2, FIN_INIT));
+  int64_t enq = 0;
+  int batch = 2, slot = 0;
+  bool have_prev = false, stop = false;
+  while (!stop) {
+    int64_t todo = std::min<int64_t>(batch, maxiter - enq);
+    for (int64_t it = 0; it < todo; ++it) {
+      mg_vcycle(h, h->r);
+      const double *z = M.lev[0].x;
+      k_mgpcg_rz<<<vg, kBlock, 0, st>>>(n, h->r, z, h->partials, h->ticket, h->scal, fin);
+      h->tm.kernel_launches++;
+      if (!fin) FVB_TRY(allreduce_fin(h, 1, FIN_RZ));
+      k_mgpcg_update_u<<<vg, kBlock, 0, st>>>(n, z, h->u, h->x, h->scal);
+      h->tm.kernel_launches++;
+      FVB_TRY(launch_spmv(h, h->u, h->c, 0.0, true));
+      if (!fin) FVB_TRY(allreduce_fin(h, 1, FIN_UC));
+      k_mgpcg_update_r<<<vg, kBlock, 0, st>>>(n, h->c, h->r, h->partials, h->ticket, h->scal, h->hist, fin);
+      h->tm.kernel_launches++;
+      if (!fin) FVB_TRY(allreduce_fin(h, 1, FIN_R));
+    }
+    enq += todo;
+    FVB_CUDA(cudaMemcpyAsync(&h->scal_host[slot], h->scal, sizeof(PcgScal), cudaMemcpyDeviceToHost, st));
+    FVB_CUDA(cudaEventRecord(h->ev[6 + slot], st));
+    if (have_prev) {
+      FVB_CUDA(cudaEventSynchronize(h->ev[6 + (slot ^ 1)]));
+      if (h->scal_host[slot ^ 1].done) stop = true;
+    }
+    have_prev = true;
+    slot ^= 1;
+    if (enq >= maxiter) stop = true;
   }
   k_finish_x<<<vg, kBlock, 0, st>>>(n, h->u, h->x, h->scal);
   h->tm.kernel_launches++;
@@ -454,6 +643,7 @@ int fvb_destroy(fvb_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   free_problem(h);
+  delete h->mg;
   if (h->peer) {
     for (int r = 0; r < kMaxRanks; ++r) {
       if (h->peer->opened_u[r]) cudaIpcCloseMemHandle(h->peer->opened_u[r]);
@@ -723,6 +913,7 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
     h->tm.kernel_launches++;
   }
   if (h->fmt_request != 1) A_TRY(build_dia(h, true));
+  if (h->precond_request == 1) A_TRY(mg_setup(h, true));
   A_CUDA(cudaEventRecord(h->ev[2], st));
   A_CUDA(cudaStreamSynchronize(st));
   A_CUDA(cudaGetLastError());
@@ -768,6 +959,7 @@ int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk
     h->tm.kernel_launches++;
   }
   if (h->dia_on) build_dia(h, false);
+  if (h->mg && h->mg->ready) mg_setup(h, false);
   cudaEventRecord(h->ev[2], st);
   int herr[ERR_COUNT];
   cudaMemcpyAsync(herr, d_err, sizeof(herr), cudaMemcpyDeviceToHost, st);
@@ -969,9 +1161,10 @@ int fvb_solve(fvb_handle h, double rtol, int64_t maxiter, const double *x0_free,
   if (x0_free) FVB_CUDA(cudaMemcpyAsync(h->x, x0_free, sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
   int64_t it = 0;
   int conv = 0;
-  double *saveD = h->Dvec;  // the steady operator is A itself
-  FVB_TRY(pcg_run(h, h->b, x0_free != nullptr, 0.0, rtol, maxiter, &it, &conv));
-  h->Dvec = saveD;
+  if (h->precond_request == 1 && h->mg && h->mg->ready && h->fmt_request != 1)
+    FVB_TRY(pcg_mg_run(h, h->b, x0_free != nullptr, rtol, maxiter, &it, &conv));
+  else
+    FVB_TRY(pcg_run(h, h->b, x0_free != nullptr, 0.0, rtol, maxiter, &it, &conv));
   FVB_CUDA(cudaEventRecord(h->ev[4], st));
   if (head_nodes) {
     double *d_head = nullptr;
@@ -1155,6 +1348,33 @@ int fvb_get_spmv_format(fvb_handle h, int *active, int *n_offsets) {
   const bool dia = h->dia_on && h->fmt_request != 1;
   if (active) *active = dia ? 2 : 1;
   if (n_offsets) *n_offsets = dia ? h->dia_K : 0;
+  return FVB_OK;
+}
+
+int fvb_set_preconditioner(fvb_handle h, int kind, int nu, double omega, double oc) {
+  FVB_TRY(check_handle(h, false));
+  if (kind != 0 && kind != 1) return set_error(FVB_ERR_BAD_INPUT, "preconditioner kind must be 0 (Jacobi) or 1 (multigrid)");
+  if (nu < 0 || nu > 8 || omega < 0 || omega >= 2 || oc < 0) return set_error(FVB_ERR_BAD_INPUT, "bad multigrid parameters");
+  h->precond_request = kind;
+  if (nu > 0) h->mg_nu = nu;
+  if (omega > 0) h->mg_omega = omega;
+  if (oc > 0) h->mg_oc = oc;
+  if (kind == 1 && h->assembled) {
+    if (!h->mg || !h->mg->ready) FVB_TRY(mg_setup(h, true));
+    FVB_CUDA(cudaStreamSynchronize(h->stream));
+    if (!h->mg->ready) {
+      h->precond_request = 0;
+      return set_error(FVB_ERR_BAD_INPUT, "multigrid needs a box-structured 7-point matrix (diagonal format with offsets 1, nz, ny*nz)");
+    }
+  }
+  return FVB_OK;
+}
+
+int fvb_get_preconditioner(fvb_handle h, int *active_kind, int *n_levels) {
+  FVB_TRY(check_handle(h, true));
+  const bool mg = h->precond_request == 1 && h->mg && h->mg->ready && h->fmt_request != 1;
+  if (active_kind) *active_kind = mg ? 1 : 0;
+  if (n_levels) *n_levels = mg ? h->mg->nlev : 0;
   return FVB_OK;
 }
 

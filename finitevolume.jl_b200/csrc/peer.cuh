@@ -17,6 +17,7 @@
 // Every spin is bounded (kPeerTimeoutNs); on timeout the solve is flagged and stops.
 #pragma once
 #include "common.cuh"
+#include "mg.cuh"
 #include "pcg.cuh"
 
 namespace fvb {
@@ -96,7 +97,7 @@ __global__ void k_halo_wait(PeerMail *mail, HaloPlanDev P, unsigned long long se
 }
 
 // ---- all-reduce of <= 4 doubles + recurrence update -------------------------------------------------
-enum { FIN_NONE = 0, FIN_INIT = 1, FIN_UC = 2, FIN_ITER = 3 };
+enum { FIN_NONE = 0, FIN_INIT = 1, FIN_UC = 2, FIN_ITER = 3, FIN_RZ = 4, FIN_R = 5 };
 
 __global__ void k_allreduce_fin(PeerTable T, unsigned long long seq, double *red, int count, int mode,
                                 PcgScal *scal, double *hist) {
@@ -124,6 +125,8 @@ __global__ void k_allreduce_fin(PeerTable T, unsigned long long seq, double *red
     if (mode == FIN_INIT) pcg_finish_init(scal, s[0], s[1]);
     else if (mode == FIN_UC) { if (!scal->done) scal->uc = s[0]; }
     else if (mode == FIN_ITER) { if (!scal->done) pcg_finish_iter(scal, s[0], s[1], hist); }
+    else if (mode == FIN_RZ) mgpcg_finish_rz(scal, s[0]);
+    else if (mode == FIN_R) mgpcg_finish_r(scal, s[0], hist);
   }
 }
 

@@ -180,6 +180,18 @@ int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes);
 int fvb_set_spmv_format(fvb_handle h, int fmt);
 int fvb_get_spmv_format(fvb_handle h, int *active, int *n_offsets);
 
+/* ---- preconditioner ----------------------------------------------------------------------
+ * kind 0: Jacobi (default; north_star).  kind 1: aggregation-multigrid V-cycle (the reference
+ * preconditions with Ruge-Stueben AMG, src/FiniteVolume.jl:160); needs a box-structured matrix
+ * (diagonal format, 3 offsets).  nu = smoothing sweeps per side (>=1), omega = Jacobi damping,
+ * oc = coarse-correction scaling; pass 0 for the defaults (2, 0.8, 1.5).
+ * Called after fvb_assemble it fails with FVB_ERR_BAD_INPUT when the matrix does not qualify;
+ * set before, fvb_assemble falls back to Jacobi silently -- check fvb_get_preconditioner.
+ * Multi-GPU: every rank applies the multigrid of its own diagonal block.  The transient step
+ * (fvb_step) always uses Jacobi. */
+int fvb_set_preconditioner(fvb_handle h, int kind, int nu, double omega, double oc);
+int fvb_get_preconditioner(fvb_handle h, int *active_kind, int *n_levels);
+
 /* ---- measurement hooks (CUDA events on the handle's own stream) ------------------- */
 /* Average device time of one SpMV launch (K5) / one PCG iteration over `reps` launches
  * on resident data, after `warmup` untimed ones. */

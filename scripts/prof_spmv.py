@@ -32,3 +32,12 @@ print(f"n={n} Nf={sz['nf_local']} nnz={sz['nnz_local']} assemble(wall incl. H2D)
 head, x, ch = s.solve(maxiter=iters)
 tm = s.timings()
 print(f"pcg {ch.iters} its: {tm['solve_ms'] / max(ch.iters, 1):.4f} ms/it")
+s.set_preconditioner("mg")
+print("preconditioner:", s.preconditioner())
+import time as _t
+for rep in range(2):
+    t0 = _t.perf_counter()
+    head2, x2, ch2 = s.solve(maxiter=max(iters, 200))
+    tm = s.timings()
+    print(f"mg-pcg: {ch2.iters} its converged={ch2.isconverged} solve={tm['solve_ms']:.1f} ms "
+          f"({tm['solve_ms'] / max(ch2.iters, 1):.2f} ms/it) wall={_t.perf_counter() - t0:.3f}s resnorm[-1]={ch2.data['resnorm'][-1]:.3e}")
