@@ -38,6 +38,11 @@ def main():
     s.assemble(nb, aol, kf, src_all[lo - 1:hi], dn, dh, None, True, n_nodes=N, node_range=(lo, hi))
     fvd.exchange_halo_plan(s)
     head, x, ch = s.solve(rtol=1e-12, want_x=True)
+    # multigrid: every rank preconditions with the V-cycle of its own diagonal block
+    s.set_preconditioner("mg")
+    head_mg, _, ch_mg = s.solve(rtol=1e-12)
+    mg_kind = s.preconditioner()[0]
+    s.set_preconditioner("jacobi")
     # distributed SpMV of a known vector
     sz = s.sizes()
     xg = np.sin(np.arange(sz["nf_global"]) * 0.37) + 2.0
@@ -50,7 +55,8 @@ def main():
     dnorm = s.vec_diffnorm(1, 2)
     step_loc = s.vec_download(2)
     out = [None] * world
-    dist.all_gather_object(out, (head, y_loc, ch.iters, ch.isconverged, step_loc, dnorm, conv_t))
+    dist.all_gather_object(out, (head, y_loc, ch.iters, ch.isconverged, step_loc, dnorm, conv_t, head_mg, ch_mg.iters,
+                                 ch_mg.isconverged, mg_kind))
     ok = True
     if rank == 0:
         from oracle import fv_oracle as orc
@@ -70,12 +76,16 @@ def main():
         sg = np.concatenate([o[4] for o in out])
         err_s = np.max(np.abs(sg - ref)) / np.max(np.abs(ref))
         dn_ref = np.linalg.norm(sg - 0.5)
+        hmg = np.concatenate([o[7] for o in out])
+        err_mg = np.max(np.abs(hmg - ho)) / np.max(np.abs(ho))
+        mg_ok = (err_mg <= 1e-8 and all(o[9] for o in out) and len({o[8] for o in out}) == 1
+                 and all(o[10] == "mg" for o in out) and out[0][8] < out[0][2])
         iters = {o[2] for o in out}
         ok = (err_h <= 1e-8 and err_y <= 1e-12 and err_s <= 1e-8 and len(iters) == 1 and all(o[3] for o in out)
               and abs(out[0][5] - dn_ref) <= 1e-10 * dn_ref and all(o[6] for o in out)
-              and abs(out[0][2] - cho.iters) <= 3)
+              and abs(out[0][2] - cho.iters) <= 3 and mg_ok)
         print(f"MGPU world={world} ns={ns} err_head={err_h:.2e} err_spmv={err_y:.2e} err_step={err_s:.2e} "
-              f"iters={sorted(iters)} oracle_iters={cho.iters} ok={ok}", flush=True)
+              f"iters={sorted(iters)} oracle_iters={cho.iters} mg_iters={out[0][8]} err_mg={err_mg:.2e} ok={ok}", flush=True)
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
     dist.barrier()
