@@ -48,6 +48,46 @@ class ConvergenceHistory:
     data: dict = field(default_factory=dict)
 
 
+class DeviceArray:
+    """A plain device allocation owned through the library (fvb_device_alloc/free): what the
+    device-side grid helpers return and what System.assemble accepts in place of numpy arrays."""
+
+    def __init__(self, system, shape, dtype):
+        self.system, self.shape, self.dtype = system, tuple(int(v) for v in np.atleast_1d(shape)), np.dtype(dtype)
+        self.size = int(np.prod(self.shape))
+        self.nbytes = self.size * self.dtype.itemsize
+        p = C.c_void_p()
+        check(lib().fvb_device_alloc(system._h, C.c_int64(self.nbytes), C.byref(p)))
+        self.ptr = p.value or 0
+
+    def to_host(self):
+        out = np.empty(self.shape, self.dtype)
+        if self.nbytes:
+            check(lib().fvb_device_copy(self.system._h, ptr(out), C.c_void_p(self.ptr), C.c_int64(self.nbytes)))
+        return out
+
+    def free(self):
+        if self.ptr and self.system._h:
+            lib().fvb_device_free(self.system._h, C.c_void_p(self.ptr))
+        self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _arg(a, dtype):
+    """-> (void*, element count, keep-alive) for a numpy-like input or a DeviceArray."""
+    if isinstance(a, DeviceArray):
+        if a.dtype != np.dtype(dtype):
+            raise TypeError(f"device array has dtype {a.dtype}, expected {np.dtype(dtype)}")
+        return C.c_void_p(a.ptr), a.size, a
+    arr = np.ascontiguousarray(np.asarray(a, dtype=dtype)).reshape(-1)
+    return ptr(arr), arr.size, arr
+
+
 class System:
     """One assembled problem resident on one GPU (an fvb_handle)."""
 
@@ -89,27 +129,27 @@ class System:
         """assembleA + assembleb (src/FiniteVolume.jl:75-139).  With node_range=(lo,hi)
         (1-based inclusive) `sources` is the owned slice and `neighbors` etc. are the faces
         touching owned nodes, in global face order."""
-        nb = _pairs(neighbors)
-        F = nb.size // 2
-        aol = f64(areasoverlengths)
-        cond = f64(conductivities)
-        src = f64(sources)
+        nb_p, nb_n, k0 = _arg(neighbors, np.int64)
+        F = nb_n // 2
+        aol_p, aol_n, k1 = _arg(areasoverlengths, np.float64)
+        cond_p, cond_n, k2 = _arg(conductivities, np.float64)
+        src_p, src_n, k3 = _arg(sources, np.float64)
         dn = i64(dirichletnodes)
         dh = f64(dirichletheads)
-        if aol.size != F:
+        if aol_n != F:
             raise ValueError("areasoverlengths and neighbors differ in length")
         if dn.size != dh.size:
             raise ValueError("dirichletnodes and dirichletheads differ in length")
         meta = _metaindex_table(metaindex, F)
-        if meta is None and cond.size < F:
+        if meta is None and cond_n < F:
             raise IndexError("conductivities is shorter than neighbors")  # Julia: BoundsError
-        N = int(src.size if n_nodes is None else n_nodes)
+        N = int(src_n if n_nodes is None else n_nodes)
         lo, hi = (1, N) if node_range is None else (int(node_range[0]), int(node_range[1]))
-        if src.size != hi - lo + 1:
+        if src_n != hi - lo + 1:
             raise ValueError("sources must cover exactly the owned node range")
-        check(lib().fvb_assemble(self._h, C.c_int64(N), C.c_int64(lo), C.c_int64(hi), C.c_int64(F), ptr(nb), ptr(aol),
-                                 ptr(cond), C.c_int64(cond.size), ptr(meta), C.c_int(int(bool(logtransformconductivity))),
-                                 ptr(src), C.c_int64(dn.size), ptr(dn), ptr(dh)))
+        check(lib().fvb_assemble(self._h, C.c_int64(N), C.c_int64(lo), C.c_int64(hi), C.c_int64(F), nb_p, aol_p,
+                                 cond_p, C.c_int64(cond_n), ptr(meta), C.c_int(int(bool(logtransformconductivity))),
+                                 src_p, C.c_int64(dn.size), ptr(dn), ptr(dh)))
         self.node_lo, self.node_hi = lo, hi
         self._logk = bool(logtransformconductivity)
         return self
@@ -135,6 +175,34 @@ class System:
         check(lib().fvb_solve(self._h, C.c_double(rtol), C.c_int64(int(maxiter)), vp(x0_ptr), vp(head_ptr), vp(x_ptr),
                               C.byref(iters), C.byref(conv), None, C.c_int64(0)))
         return int(iters.value), bool(conv.value)
+
+    # ---- device-side grid helpers (src/grid.jl) ---------------------------------------------
+    def device_regulargrid(self, mins, maxs, ns, planes=None, want_volumes=True):
+        """regulargrid (src/grid.jl:56-110) generated on the GPU -> (neighbors, areasoverlengths, volumes)
+        as DeviceArrays, bit-identical to the host builder; planes=(lo,hi) restricts to a slab."""
+        if len(mins) != 3 or len(maxs) != 3 or len(ns) != 3:
+            raise ValueError("only 3 dimensions supported")
+        mn, mx, nn = f64(mins), f64(maxs), i64(ns)
+        lo, hi = (1, int(nn[0])) if planes is None else (int(planes[0]), int(planes[1]))
+        F = C.c_int64()
+        check(lib().fvb_regulargrid(self._h, ptr(mn), ptr(mx), ptr(nn), C.c_int64(lo), C.c_int64(hi), C.byref(F), None,
+                                    None, None))
+        nb = DeviceArray(self, (F.value, 2), np.int64)
+        aol = DeviceArray(self, (F.value,), np.float64)
+        vol = DeviceArray(self, ((hi - lo + 1) * int(nn[1]) * int(nn[2]),), np.float64) if want_volumes else None
+        check(lib().fvb_regulargrid(self._h, ptr(mn), ptr(mx), ptr(nn), C.c_int64(lo), C.c_int64(hi), C.byref(F),
+                                    C.c_void_p(nb.ptr), C.c_void_p(aol.ptr), C.c_void_p(vol.ptr) if vol else None))
+        return nb, aol, vol
+
+    def device_nodehycos2neighborhycos(self, neighbors_dev, nodehycos, logtransformhyco=False, node_lo=1):
+        """nodehycos2neighborhycos (src/grid.jl:14-33) on the GPU; nodehycos covers nodes node_lo.. in node order."""
+        k = np.asarray(nodehycos, np.float64)
+        flat = np.ascontiguousarray(k.reshape(-1, order="F") if k.ndim == 3 else k.reshape(-1))
+        out = DeviceArray(self, (neighbors_dev.shape[0],), np.float64)
+        check(lib().fvb_nodehycos2neighborhycos(self._h, C.c_int64(neighbors_dev.shape[0]), C.c_void_p(neighbors_dev.ptr),
+                                                ptr(flat), C.c_int64(int(node_lo)), C.c_int64(flat.size),
+                                                C.c_int(int(bool(logtransformhyco))), C.c_void_p(out.ptr)))
+        return out
 
     def update_values(self, conductivities, sources=None, dirichletheads=None, logtransformconductivity=None):
         cond = f64(conductivities)

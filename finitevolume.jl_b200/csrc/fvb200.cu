@@ -12,6 +12,7 @@
 #include "assemble.cuh"
 #include "common.cuh"
 #include "dia.cuh"
+#include "grid.cuh"
 #include "nccl_dyn.h"
 #include "pcg.cuh"
 #include "peer.cuh"
@@ -1348,6 +1349,81 @@ int fvb_get_spmv_format(fvb_handle h, int *active, int *n_offsets) {
   const bool dia = h->dia_on && h->fmt_request != 1;
   if (active) *active = dia ? 2 : 1;
   if (n_offsets) *n_offsets = dia ? h->dia_K : 0;
+  return FVB_OK;
+}
+
+int fvb_device_alloc(fvb_handle h, int64_t bytes, void **dev_ptr) {
+  FVB_TRY(check_handle(h, false));
+  if (bytes < 0 || !dev_ptr) return set_error(FVB_ERR_BAD_INPUT, "bad allocation request");
+  unsigned char *p = nullptr;
+  FVB_TRY(dalloc(h, &p, bytes));
+  FVB_CUDA(cudaStreamSynchronize(h->stream));
+  *dev_ptr = p;
+  return FVB_OK;
+}
+
+int fvb_device_free(fvb_handle h, void *dev_ptr) {
+  FVB_TRY(check_handle(h, false));
+  if (dev_ptr) FVB_CUDA(cudaFreeAsync(dev_ptr, h->stream));
+  return FVB_OK;
+}
+
+int fvb_device_copy(fvb_handle h, void *dst, const void *src, int64_t bytes) {
+  FVB_TRY(check_handle(h, false));
+  FVB_CUDA(memcpy_sync(h->stream, dst, src, (size_t)bytes, cudaMemcpyDefault));
+  return FVB_OK;
+}
+
+int fvb_regulargrid(fvb_handle h, const double mins[3], const double maxs[3], const int64_t ns[3], int64_t plane_lo,
+                    int64_t plane_hi, int64_t *n_faces, int64_t *neighbors, double *aol, double *volumes) {
+  FVB_TRY(check_handle(h, false));
+  if (!mins || !maxs || !ns) return set_error(FVB_ERR_BAD_INPUT, "null grid description");
+  if (ns[0] < 2 || ns[1] < 2 || ns[2] < 2) return set_error(FVB_ERR_BAD_INPUT, "regulargrid needs at least 2 points per axis");
+  if (plane_lo < 1 || plane_hi > ns[0] || plane_hi < plane_lo) return set_error(FVB_ERR_BAD_INPUT, "bad plane range");
+  GridDesc G;
+  G.n1 = ns[0]; G.n2 = ns[1]; G.n3 = ns[2];
+  // range(lo; stop=hi, length=n): dx = xs[2] - xs[1]   (src/grid.jl:62-67)
+  auto axis = [](double lo, double hi, int64_t n) { double step = (hi - lo) / (double)(n - 1); return (lo + 1 * step) - lo; };
+  G.dx = axis(mins[0], maxs[0], ns[0]); G.dy = axis(mins[1], maxs[1], ns[1]); G.dz = axis(mins[2], maxs[2], ns[2]);
+  G.p_lo = plane_lo; G.p_hi = plane_hi; G.e_lo = plane_lo > 1 ? plane_lo - 1 : plane_lo;
+  const int64_t plane = G.n2 * G.n3, pfull = plane + (G.n2 - 1) * G.n3 + G.n2 * (G.n3 - 1);
+  int64_t F = (G.e_lo < G.p_lo ? plane : 0);
+  for (int64_t i1 = plane_lo; i1 <= plane_hi; ++i1) F += pfull - (i1 < G.n1 ? 0 : plane);
+  if (n_faces) *n_faces = F;
+  if (!neighbors) return FVB_OK;
+  if (!aol) return set_error(FVB_ERR_BAD_INPUT, "null areasoverlengths buffer");
+  const int64_t nodes = (G.p_hi - G.e_lo + 1) * plane;
+  k_regulargrid<<<std::max(1, std::min(cdiv(nodes, kBlock), h->num_sms * 16)), kBlock, 0, h->stream>>>(
+      G, reinterpret_cast<longlong2 *>(neighbors), aol, volumes);
+  h->tm.kernel_launches++;
+  FVB_CUDA(cudaStreamSynchronize(h->stream));
+  FVB_CUDA(cudaGetLastError());
+  return FVB_OK;
+}
+
+int fvb_nodehycos2neighborhycos(fvb_handle h, int64_t n_faces, const int64_t *neighbors_dev, const double *nodehycos,
+                                int64_t node_lo, int64_t n_have, int logmean, double *out_dev) {
+  FVB_TRY(check_handle(h, false));
+  if (n_faces < 0 || n_have < 0 || (n_faces && (!neighbors_dev || !nodehycos || !out_dev)))
+    return set_error(FVB_ERR_BAD_INPUT, "bad arguments");
+  cudaStream_t st = h->stream;
+  double *d_k = nullptr;
+  int *d_err = nullptr;
+  FVB_TRY(dalloc(h, &d_k, n_have));
+  FVB_TRY(dalloc(h, &d_err, 1));
+  int init = INT_MAX;
+  cudaMemcpyAsync(d_err, &init, sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_k, nodehycos, sizeof(double) * (size_t)n_have, cudaMemcpyDefault, st);
+  if (n_faces) {
+    k_node2face<<<std::max(1, std::min(cdiv(n_faces, kBlock), h->num_sms * 16)), kBlock, 0, st>>>(
+        n_faces, reinterpret_cast<const longlong2 *>(neighbors_dev), d_k, node_lo, n_have, logmean, out_dev, d_err);
+    h->tm.kernel_launches++;
+  }
+  int bad = INT_MAX;
+  cudaError_t e = memcpy_sync(st, &bad, d_err, sizeof(int), cudaMemcpyDeviceToHost);
+  dfree(h, d_k); dfree(h, d_err);
+  if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+  if (bad != INT_MAX) return set_error(FVB_ERR_BAD_INPUT, "face " + std::to_string(bad + 1) + " references a node outside the supplied nodehycos range");
   return FVB_OK;
 }
 

@@ -180,6 +180,26 @@ int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes);
 int fvb_set_spmv_format(fvb_handle h, int fmt);
 int fvb_get_spmv_format(fvb_handle h, int *active, int *n_offsets);
 
+/* ---- device-side grid helpers (src/grid.jl:56-110, :14-33) ---------------------------------
+ * Same ordering and bit-identical values as the reference's serial loops, produced directly in
+ * device memory (the host never holds the neighbor list).  Buffers are plain device allocations
+ * owned by the caller through fvb_device_alloc/free; they can be passed to fvb_assemble as is.
+ *   plane_lo/hi  1-based inclusive x-planes this rank owns (1, ns[0] for the whole grid); the output
+ *                is every face with an endpoint in those planes, in global face order
+ *   n_faces      out; call with neighbors == NULL first to query it
+ *   volumes      [ (plane_hi-plane_lo+1)*ns[1]*ns[2] ] or NULL */
+int fvb_device_alloc(fvb_handle h, int64_t bytes, void **dev_ptr);
+int fvb_device_free(fvb_handle h, void *dev_ptr);
+int fvb_device_copy(fvb_handle h, void *dst, const void *src, int64_t bytes); /* any direction */
+int fvb_regulargrid(fvb_handle h, const double mins[3], const double maxs[3], const int64_t ns[3],
+                    int64_t plane_lo, int64_t plane_hi, int64_t *n_faces, int64_t *neighbors,
+                    double *aol, double *volumes);
+/* nodehycos: values of nodes node_lo..node_lo+n_have-1 (1-based, node order; host or device);
+ * out[i] = logmean ? (k1+k2)/2 : sqrt(k1*k2) for the n_faces device-resident neighbor pairs. */
+int fvb_nodehycos2neighborhycos(fvb_handle h, int64_t n_faces, const int64_t *neighbors_dev,
+                                const double *nodehycos, int64_t node_lo, int64_t n_have, int logmean,
+                                double *out_dev);
+
 /* ---- preconditioner ----------------------------------------------------------------------
  * kind 0: Jacobi (default; north_star).  kind 1: aggregation-multigrid V-cycle (the reference
  * preconditions with Ruge-Stueben AMG, src/FiniteVolume.jl:160); needs a box-structured matrix

@@ -513,3 +513,41 @@ def test_multigrid_odd_sizes_and_high_contrast(fv, orc):
                                       precond="mg")
         assert ch.isconverged and ch.iters < cho.iters
         assert np.max(np.abs(h - ho)) <= 1e-8 * np.max(np.abs(ho))
+
+
+@pytest.mark.parametrize("mins,maxs,ns", [([0, 0, 0], [3, 2, 1], [4, 3, 2]), ([-50, -50, 0], [50, 50, 10], [20, 10, 2]),
+                                          ([0, 0, 0], [8, 6, 4], [9, 7, 5])])
+def test_device_grid_generator(fv, orc, mins, maxs, ns):
+    """regulargrid / nodehycos2neighborhycos generated on the GPU must be bit-identical to
+    the serial loops of src/grid.jl (oracle) -- whole grid and every slab -- and feed assemble directly."""
+    import importlib
+    dist = importlib.import_module("fvb200.distributed")
+    _, nbo, aolo, volo = orc.regulargrid(mins, maxs, ns, want_coords=False)
+    s = fv.System()
+    nb, aol, vol = s.device_regulargrid(mins, maxs, ns)
+    assert np.array_equal(nb.to_host(), nbo) and np.array_equal(aol.to_host(), aolo) and np.array_equal(vol.to_host(), volo)
+    N = int(np.prod(ns))
+    k = np.random.default_rng(0).random(N) + 0.1
+    for lg in (False, True):
+        kf = s.device_nodehycos2neighborhycos(nb, k, lg)
+        assert np.array_equal(kf.to_host(), orc.nodehycos2neighborhycos(nbo, k, lg))
+    for nranks in (2, 3):
+        if ns[0] < nranks:
+            continue
+        for pl in dist.slab_planes(ns[0], nranks):
+            lo, hi = dist.node_range_of_planes(pl, ns[1], ns[2])
+            touch = ((nbo[:, 0] >= lo) & (nbo[:, 0] <= hi)) | ((nbo[:, 1] >= lo) & (nbo[:, 1] <= hi))
+            nbs, aols, vols = s.device_regulargrid(mins, maxs, ns, planes=pl)
+            assert np.array_equal(nbs.to_host(), nbo[touch]) and np.array_equal(aols.to_host(), aolo[touch])
+            assert np.array_equal(vols.to_host(), volo[lo - 1:hi])
+    # device arrays go straight into assemble: same CSR as from host lists
+    plane = ns[1] * ns[2]
+    dn = np.concatenate([np.arange(1, plane + 1), np.arange(N - plane + 1, N + 1)])
+    dh = np.concatenate([np.ones(plane), np.zeros(plane)])
+    kf = s.device_nodehycos2neighborhycos(nb, np.log(k), True)
+    s.assemble(nb, aol, kf, np.zeros(N), dn, dh, None, True)
+    Ao = orc.assembleA(nbo, aolo, orc.nodehycos2neighborhycos(nbo, np.log(k), True), np.zeros(N), dn, dh, None, True)
+    p, i, v = s.csr()
+    assert np.array_equal(p, Ao.colptr) and np.array_equal(i, Ao.rowval) and np.allclose(v, Ao.nzval, rtol=1e-14, atol=0)
+    with pytest.raises(fv.FVBError, match="outside the supplied nodehycos range"):
+        s.device_nodehycos2neighborhycos(nb, k[: N // 2], False)
