@@ -85,8 +85,12 @@ def problem_inputs(fv, n, sigma, planes=None, pin=None):
         e = min(F, o + step)
         np.add(lnk[nb[o:e, 0] - 1], lnk[nb[o:e, 1] - 1], out=kf[o:e])
     kf *= 0.5
-    del lnk
     lo, hi = (planes[0] - 1) * plane + 1, planes[1] * plane
+    # node values of the slab plus one plane on each side (what the device-side grid path uploads)
+    k_lo, k_hi = max(1, lo - plane), min(N, hi + plane)
+    lnk_slab = alloc((k_hi - k_lo + 1,), np.float64)
+    lnk_slab[:] = lnk[k_lo - 1:k_hi]
+    del lnk
     src = alloc((hi - lo + 1,), np.float64)
     src[:] = 0.0
     dn = alloc((2 * plane,), np.int64)
@@ -95,7 +99,8 @@ def problem_inputs(fv, n, sigma, planes=None, pin=None):
     dh = alloc((2 * plane,), np.float64)
     dh[:plane] = 1.0
     dh[plane:] = 0.0
-    return dict(N=N, F=F, node_range=(lo, hi), nb=nb, aol=aol, kf=kf, src=src, dn=dn, dh=dh)
+    return dict(N=N, F=F, node_range=(lo, hi), nb=nb, aol=aol, kf=kf, src=src, dn=dn, dh=dh, lnk_slab=lnk_slab,
+                lnk_node_lo=k_lo)
 
 
 def spmv_bytes(nf, nnz):
@@ -306,6 +311,24 @@ def main():
         wall_parts.update(assemble_call_s=t1 - t0, halo_plan_s=t2 - t1, solve_call_s=time.perf_counter() - t2)
         return it, conv
 
+    def step_devgrid(head_ptr):
+        """Same solve, but the grid never exists on the host: upload the node ln K of the slab (+1 plane each
+        side), build neighbors / areasoverlengths / face K on the device (fvb_regulargrid,
+        fvb_nodehycos2neighborhycos), assemble from those device arrays."""
+        t0 = time.perf_counter()
+        nbd, aold, _ = sysm.device_regulargrid([0, 0, 0], [n - 1] * 3, [n, n, n], planes=mine, want_volumes=False)
+        t1 = time.perf_counter()
+        kfd = sysm.device_nodehycos2neighborhycos(nbd, P["lnk_slab"], True, node_lo=P["lnk_node_lo"])
+        t2 = time.perf_counter()
+        sysm.assemble_raw(P["N"], lo, hi, nbd.shape[0], nbd.ptr, aold.ptr, kfd.ptr, nbd.shape[0], 0, True,
+                          host_ptrs["src"], P["dn"].size, host_ptrs["dn"], host_ptrs["dh"])
+        t3 = time.perf_counter()
+        if world > 1:
+            fvd.exchange_halo_plan(sysm)
+        r = sysm.solve_raw(args.rtol, args.maxiter, head_ptr=head_ptr)
+        wall_parts.update(grid_s=t1 - t0, facek_s=t2 - t1, assemble_call_s=t3 - t2, solve_call_s=time.perf_counter() - t3)
+        return r
+
     dev_ptrs = {k: v.data_ptr() for k, v in dev.items()}
     host_ptrs = {k: P[k].ctypes.data for k in ("nb", "aol", "kf", "src", "dn", "dh")}
 
@@ -350,6 +373,19 @@ def main():
     e2e_s = maxreduce((time.perf_counter() - e0) / max(args.e2e_steps, 1))
     e2e_tm = sysm.timings()
     e2e_parts = dict(wall_parts)
+    # ---- end to end with the device-side grid generator (extra information) ---------------------
+    head_e2e = head_host.numpy().copy()
+    step_devgrid(head_host.data_ptr())  # warm-up of the extra allocations
+    barrier()
+    g0 = time.perf_counter()
+    it_g, conv_g = step_devgrid(head_host.data_ptr())
+    barrier()
+    devgrid = {"value": maxreduce(time.perf_counter() - g0), "unit": "s", "pcg_iterations": it_g,
+               "h2d_bytes_per_step": int(P["lnk_slab"].nbytes + P["src"].nbytes + P["dn"].nbytes + P["dh"].nbytes),
+               "identical_heads": bool(np.array_equal(head_host.numpy(), head_e2e)), "host_wall": dict(wall_parts),
+               "solve_ms": sysm.timings()["solve_ms"], "assemble_ms": sysm.timings()["assemble_ms"],
+               "format": list(sysm.spmv_format()),
+               "note": "host uploads node ln K only; neighbors/areasoverlengths/face K generated on the device"}
 
     # ---- the other preconditioner on the same resident inputs (extra information, not the headline) ----
     alt = "mg" if args.precond == "jacobi" else "jacobi"
@@ -370,9 +406,14 @@ def main():
         barrier()
         ea = maxreduce(time.perf_counter() - ea)
         tma = sysm.timings()
+        barrier()
+        eg = time.perf_counter()
+        step_devgrid(head_host.data_ptr())
+        barrier()
+        eg = maxreduce(time.perf_counter() - eg)
         diff = float(np.max(np.abs(head_host.numpy() - head_main)))
         alt_info = {"precond": alt, "active": sysm.preconditioner()[0], "value": maxreduce(a_ms / args.steps / 1e3),
-                    "unit": "s", "e2e": ea, "pcg_iterations": it_a, "converged": bool(conv_a),
+                    "unit": "s", "e2e": ea, "e2e_device_grid": eg, "pcg_iterations": it_a, "converged": bool(conv_a),
                     "solve_ms": tma["solve_ms"], "assemble_ms": tma["assemble_ms"], "h2d_ms": tma["h2d_ms"],
                     "max_abs_head_difference_vs_headline": diff,
                     "note": "same inputs, same tolerance; heads differ by solver tolerance only"}
@@ -437,6 +478,7 @@ def main():
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "h2d_ms": e2e_tm["h2d_ms"], "assemble_ms": e2e_tm["assemble_ms"], "solve_ms": e2e_tm["solve_ms"],
                     "d2h_ms": e2e_tm["d2h_ms"], "pcg_iterations": it_e, "host_wall": e2e_parts},
+            "e2e_device_grid": devgrid,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm",
                          "kernel": ("k_spmv_dia<true,%d> (symmetric-diagonal SpMV + fused u.Au)" % fmt_k) if fmt == "dia"

@@ -18,7 +18,8 @@ SYMBOLS = [
     "fvb_version", "fvb_last_error", "fvb_device_count", "fvb_create", "fvb_destroy",
     "fvb_comm_unique_id", "fvb_comm_init", "fvb_assemble", "fvb_update_values", "fvb_sizes",
     "fvb_get_csr", "fvb_get_b", "fvb_get_diag", "fvb_get_freenode", "fvb_get_nodei2freenodei",
-    "fvb_get_halo_cols", "fvb_set_halo_plan", "fvb_peer_export", "fvb_peer_import", "fvb_solve", "fvb_spmv", "fvb_vec_upload",
+    "fvb_get_halo_cols", "fvb_set_halo_plan", "fvb_peer_export", "fvb_peer_import", "fvb_gradient_begin", "fvb_gradient_accumulate",
+    "fvb_gradient_end", "fvb_solve", "fvb_spmv", "fvb_vec_upload",
     "fvb_vec_download", "fvb_vec_copy", "fvb_vec_load_b", "fvb_vec_diffnorm", "fvb_set_storage",
     "fvb_step", "fvb_vec_to_nodes", "fvb_time_spmv", "fvb_device_alloc", "fvb_device_free", "fvb_device_copy", "fvb_regulargrid",
     "fvb_nodehycos2neighborhycos", "fvb_set_preconditioner", "fvb_get_preconditioner", "fvb_set_spmv_format", "fvb_get_spmv_format", "fvb_set_profiling", "fvb_get_timings", "fvb_sync",

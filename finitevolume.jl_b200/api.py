@@ -329,6 +329,24 @@ class System:
                              C.byref(conv)))
         return int(iters.value), bool(conv.value)
 
+    # ---- adjoint gradient gather -------------------------------------------------------------------
+    def gradient_begin(self, neighbors):
+        nb_p, _, keep = _arg(neighbors, np.int64)
+        check(lib().fvb_gradient_begin(self._h, nb_p))
+
+    def gradient_accumulate(self, u_slot, lambda_slot, weight):
+        check(lib().fvb_gradient_accumulate(self._h, C.c_int(u_slot), C.c_int(lambda_slot), C.c_double(weight)))
+
+    def gradient_end(self, n_faces):
+        """-> (per-face d/dk contributions, per-face d/dh contributions, 1-based Dirichlet slot per face or -1,
+        per-row d/dsources contributions)."""
+        gk = np.empty(n_faces, np.float64)
+        gh = np.empty(n_faces, np.float64)
+        sl = np.empty(n_faces, np.int64)
+        gs = np.empty(self.sizes()["nf_local"], np.float64)
+        check(lib().fvb_gradient_end(self._h, ptr(gk), ptr(gh), ptr(sl), ptr(gs)))
+        return gk, gh, sl, gs
+
     def vec_to_nodes(self, slot):
         out = np.empty(self.n_own_nodes, np.float64)
         check(lib().fvb_vec_to_nodes(self._h, C.c_int(slot), ptr(out)))

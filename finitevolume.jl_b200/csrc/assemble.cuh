@@ -301,6 +301,65 @@ __global__ void k_fill_tail(int *rowptr, int n, int pad) {
   for (int i = threadIdx.x; i < pad; i += blockDim.x) rowptr[n + 1 + i] = v;
 }
 
+// ---- adjoint gradient gather (src/transientadjointutils.jl:22-32) -------------------------
+// endpoints of every face as (local row | -1-dirichlet slot | INT_MIN for anything not owned)
+__global__ void k_face_endpoints(int64_t nfaces, const int64_t *__restrict__ nb, Resolver res,
+                                 int *__restrict__ e1, int *__restrict__ e2) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nfaces) return;
+  longlong2 p = reinterpret_cast<const longlong2 *>(nb)[i];
+  NodeRef a = res(p.x - 1), b = res(p.y - 1);
+  e1[i] = a.kind == 0 ? a.local : (a.kind == 1 ? -1 - a.local : INT_MIN);
+  e2[i] = b.kind == 0 ? b.local : (b.kind == 1 ? -1 - b.local : INT_MIN);
+}
+
+// One thread per face; every accumulator has a single writer.
+__global__ void k_gradient_faces(int64_t nfaces, const int *__restrict__ e1, const int *__restrict__ e2,
+                                 const double *__restrict__ cface, const double *__restrict__ aol, int logk,
+                                 const double *__restrict__ u, const double *__restrict__ lam,
+                                 const double *__restrict__ Dvec, const double *__restrict__ dheads, double w,
+                                 double *__restrict__ gface, double *__restrict__ gdh) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nfaces) return;
+  const int a = e1[i], b = e2[i];
+  if (a == INT_MIN || b == INT_MIN) return;
+  const double c = cface[i];
+  const double dc = logk ? c : aol[i];
+  if (a >= 0 && b >= 0) {
+    if (a == b) return;
+    const double la = lam[a] / (Dvec ? Dvec[a] : 1.0), lb = lam[b] / (Dvec ? Dvec[b] : 1.0);
+    gface[i] += w * (-dc * (u[a] - u[b]) * (la - lb));
+  } else if (a >= 0) {
+    const double la = lam[a] / (Dvec ? Dvec[a] : 1.0);
+    gface[i] += w * (dc * (dheads[-1 - b] - u[a]) * la);
+    gdh[i] += w * (c * la);
+  } else if (b >= 0) {
+    const double lb = lam[b] / (Dvec ? Dvec[b] : 1.0);
+    gface[i] += w * (dc * (dheads[-1 - a] - u[b]) * lb);
+    gdh[i] += w * (c * lb);
+  }
+}
+
+__global__ void k_gradient_rows(int64_t n, const double *__restrict__ lam, const double *__restrict__ Dvec, double w,
+                                double *__restrict__ gsrc) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) gsrc[r] += w * lam[r] / (Dvec ? Dvec[r] : 1.0);
+}
+
+// which Dirichlet slot a face's head-gradient belongs to (-1: none)
+__global__ void k_gradient_dslots(int64_t nfaces, const int *__restrict__ e1, const int *__restrict__ e2,
+                                  int64_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nfaces) return;
+  const int a = e1[i], b = e2[i];
+  int64_t s = -1;
+  if (a != INT_MIN && b != INT_MIN) {
+    if (a >= 0 && b < 0) s = -1 - b;
+    else if (b >= 0 && a < 0) s = -1 - a;
+  }
+  out[i] = s < 0 ? -1 : s + 1;  // 1-based on the wire
+}
+
 // ---- extraction to the Julia layout ---------------------------------------------------------------
 __global__ void k_export_ptr(const int *__restrict__ rowptr, int64_t n1, int64_t *__restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -114,6 +114,11 @@ struct fvb_handle_s {
   double *dia_U[4] = {};
   int64_t dia_lo0 = 0, dia_nlo = 0, dia_hi0 = 0, dia_nhi = 0;
 
+  // adjoint gradient accumulators (fvb_gradient_*)
+  int logk = 0;
+  int32_t *g_e1 = nullptr, *g_e2 = nullptr;   // per-face endpoints: local row >= 0, -1-slot, or INT_MIN (off-rank)
+  double *g_face = nullptr, *g_dh = nullptr, *g_src = nullptr;
+
   // preconditioner: 0 Jacobi, 1 aggregation multigrid (mg.cuh)
   int precond_request = 0;
   int mg_nu = 2;

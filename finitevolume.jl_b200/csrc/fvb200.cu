@@ -97,6 +97,7 @@ void free_problem(fvb_handle h) {
   for (auto &s : h->slots) dfree(h, s);
   dfree(h, h->partials); dfree(h, h->hist); dfree(h, h->xio); dfree(h, h->yio);
   dfree(h, h->send_rows); dfree(h, h->sendbuf);
+  dfree(h, h->g_e1); dfree(h, h->g_e2); dfree(h, h->g_face); dfree(h, h->g_dh); dfree(h, h->g_src);
   for (auto &u : h->dia_U) dfree(h, u);
   h->dia_on = false;
   h->dia_K = 0;
@@ -717,6 +718,7 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
   cudaStream_t st = h->stream;
   h->n_nodes = n_nodes; h->node_lo = node_lo1 - 1; h->node_hi = node_hi1; h->n_own_nodes = n_own;
   h->n_faces = n_faces; h->n_dirichlet = nd;
+  h->logk = logk ? 1 : 0;
   const bool whole = (h->node_lo == 0 && h->node_hi == n_nodes);
 
   // ---- host -> device ----------------------------------------------------------------------
@@ -1072,6 +1074,79 @@ int fvb_set_halo_plan(fvb_handle h, int n_peers, const int32_t *peer_ranks, cons
   FVB_CUDA(memcpy_sync(h->stream, h->send_rows, rows.data(), sizeof(int32_t) * (size_t)ns, cudaMemcpyHostToDevice));
   h->n_send = ns;
   h->halo_ready = true;
+  return FVB_OK;
+}
+
+int fvb_gradient_begin(fvb_handle h, const int64_t *neighbors) {
+  FVB_TRY(check_handle(h, true));
+  if (h->n_faces && !neighbors) return set_error(FVB_ERR_BAD_INPUT, "null neighbors");
+  if (h->nranks != 1 || h->node_lo != 0 || h->node_hi != h->n_nodes)
+    return set_error(FVB_ERR_STATE, "the gradient gather is implemented for unpartitioned problems");
+  cudaStream_t st = h->stream;
+  const int64_t F = h->n_faces, n = h->nf_local;
+  if (!h->g_e1) {
+    FVB_TRY(dalloc(h, &h->g_e1, F)); FVB_TRY(dalloc(h, &h->g_e2, F));
+    FVB_TRY(dalloc(h, &h->g_face, F)); FVB_TRY(dalloc(h, &h->g_dh, F)); FVB_TRY(dalloc(h, &h->g_src, n));
+    int64_t *d_nb = nullptr;
+    FVB_TRY(dalloc(h, &d_nb, 2 * F));
+    FVB_CUDA(cudaMemcpyAsync(d_nb, neighbors, sizeof(int64_t) * 2 * (size_t)F, cudaMemcpyDefault, st));
+    Resolver res{h->nodemap, h->n_nodes, h->node_lo, h->node_hi, nullptr, nullptr, 0};
+    if (F) {
+      k_face_endpoints<<<grid_for(F), kBlock, 0, st>>>(F, d_nb, res, h->g_e1, h->g_e2);
+      h->tm.kernel_launches++;
+    }
+    dfree(h, d_nb);
+  }
+  FVB_CUDA(cudaMemsetAsync(h->g_face, 0, sizeof(double) * (size_t)std::max<int64_t>(F, 1), st));
+  FVB_CUDA(cudaMemsetAsync(h->g_dh, 0, sizeof(double) * (size_t)std::max<int64_t>(F, 1), st));
+  FVB_CUDA(cudaMemsetAsync(h->g_src, 0, sizeof(double) * (size_t)std::max<int64_t>(n, 1), st));
+  FVB_CUDA(cudaStreamSynchronize(st));
+  return FVB_OK;
+}
+
+int fvb_gradient_accumulate(fvb_handle h, int u_slot, int lambda_slot, double weight) {
+  FVB_TRY(check_handle(h, true));
+  if (!h->g_e1) return set_error(FVB_ERR_STATE, "call fvb_gradient_begin first");
+  FVB_TRY(ensure_slot(h, u_slot));
+  FVB_TRY(ensure_slot(h, lambda_slot));
+  cudaStream_t st = h->stream;
+  if (h->n_faces) {
+    k_gradient_faces<<<grid_for(h->n_faces), kBlock, 0, st>>>(h->n_faces, h->g_e1, h->g_e2, h->cface, h->aol, h->logk,
+                                                              h->slots[u_slot], h->slots[lambda_slot], h->Dvec,
+                                                              h->dheads, weight, h->g_face, h->g_dh);
+    h->tm.kernel_launches++;
+  }
+  if (h->nf_local) {
+    k_gradient_rows<<<grid_for(h->nf_local), kBlock, 0, st>>>(h->nf_local, h->slots[lambda_slot], h->Dvec, weight,
+                                                              h->g_src);
+    h->tm.kernel_launches++;
+  }
+  return FVB_OK;
+}
+
+int fvb_gradient_end(fvb_handle h, double *grad_cond_face, double *grad_dhead_face, int64_t *dhead_slot_face,
+                     double *grad_source_rows) {
+  FVB_TRY(check_handle(h, true));
+  if (!h->g_e1) return set_error(FVB_ERR_STATE, "call fvb_gradient_begin first");
+  cudaStream_t st = h->stream;
+  const size_t F = (size_t)h->n_faces;
+  if (grad_cond_face) FVB_CUDA(cudaMemcpyAsync(grad_cond_face, h->g_face, sizeof(double) * F, cudaMemcpyDefault, st));
+  if (grad_dhead_face) FVB_CUDA(cudaMemcpyAsync(grad_dhead_face, h->g_dh, sizeof(double) * F, cudaMemcpyDefault, st));
+  if (grad_source_rows)
+    FVB_CUDA(cudaMemcpyAsync(grad_source_rows, h->g_src, sizeof(double) * (size_t)h->nf_local, cudaMemcpyDefault, st));
+  if (dhead_slot_face) {
+    int64_t *d_s = nullptr;
+    FVB_TRY(dalloc(h, &d_s, h->n_faces));
+    if (F) {
+      k_gradient_dslots<<<grid_for(h->n_faces), kBlock, 0, st>>>(h->n_faces, h->g_e1, h->g_e2, d_s);
+      h->tm.kernel_launches++;
+    }
+    cudaError_t e = cudaMemcpyAsync(dhead_slot_face, d_s, sizeof(int64_t) * F, cudaMemcpyDefault, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    dfree(h, d_s);
+    if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+  }
+  FVB_CUDA(cudaStreamSynchronize(st));
   return FVB_OK;
 }
 

@@ -242,3 +242,106 @@ def adjointintegrate(getdgdu, tspan, Ss, volumes, neighbors, areasoverlengths, c
         return gammas[::-1], [tspan[1] - t for t in tsg][::-1]
     finally:
         sysm.close()
+
+
+# ======================================================================================================
+# Adjoint gradient: src/transientadjointutils.jl + gradientintegrate (src/transient.jl:207-216)
+# ======================================================================================================
+def getcontinuoussolution(us, ts):
+    """src/transient.jl:176-180: piecewise-linear interpolant t -> u(t) of the stored states
+    (Interpolations.Gridded(Linear()))."""
+    ts = np.asarray(ts, np.float64)
+    asc = ts if ts[0] <= ts[-1] else ts[::-1]
+    vals = us if ts[0] <= ts[-1] else us[::-1]
+
+    def uc(t):
+        j = int(np.clip(np.searchsorted(asc, t, side="right") - 1, 0, len(asc) - 2))
+        w = (t - asc[j]) / (asc[j + 1] - asc[j])
+        return (1 - w) * np.asarray(vals[j]) + w * np.asarray(vals[j + 1])
+    return uc
+
+
+def _simpson_nodes(grids, t0, t1):
+    """Quadrature nodes/weights that integrate products of functions piecewise linear on the given
+    grids exactly over [t0, t1] (Simpson on the merged grid; the reference uses adaptive QuadGK)."""
+    pts = np.unique(np.concatenate([np.asarray(g, np.float64) for g in grids] + [[t0, t1]]))
+    pts = pts[(pts >= t0) & (pts <= t1)]
+    w = {}
+    for a, b in zip(pts[:-1], pts[1:]):
+        h = b - a
+        for t, c in ((a, h / 6), (0.5 * (a + b), 4 * h / 6), (b, h / 6)):
+            w[t] = w.get(t, 0.0) + c
+    ts = sorted(w)
+    return ts, [w[t] for t in ts]
+
+
+def getadjointfunctions(sigma, obsfreenodes, uobs, dirichletnodes, n_nodes, device=0):
+    """g and dg/du of src/transientadjointutils.jl:4-21: g(u,t) = sum_i sigma(i,t)^2 (u_i - uobs_i)^2 over the
+    observed free rows i (u, uobs: callables t -> length-N node vectors).  Returns (g, dgdu)."""
+    from .api import getfreenodes
+    freenode, n2f = getfreenodes(n_nodes, dirichletnodes, device=device)
+    f2n = np.nonzero(freenode)[0]  # 0-based node of free row (1-based row r -> f2n[r-1])
+    nf = int(freenode.sum())
+
+    def g(u, t):
+        ue, uo = u(t), uobs(t)
+        return float(sum(sigma(i, t) ** 2 * (ue[f2n[i - 1]] - uo[f2n[i - 1]]) ** 2 for i in obsfreenodes))
+
+    def dgdu(u, t):
+        ue, uo = u(t), uobs(t)
+        out = np.zeros(nf)
+        for i in obsfreenodes:
+            out[i - 1] = 2 * sigma(i, t) ** 2 * (ue[f2n[i - 1]] - uo[f2n[i - 1]])
+        return out
+    return g, dgdu
+
+
+def integrate_g(g, u, grids, tspan):
+    """G = int g(u,t) dt (the `G` of getadjointfunctions, :42-54), exact for piecewise-linear u/uobs."""
+    ts, ws = _simpson_nodes(grids, tspan[0], tspan[1])
+    return float(sum(w * g(u, t) for t, w in zip(ts, ws)))
+
+
+def integratedfdplambda(us, ts, lambdas, ts_lambda, tspan, Ss, volumes, neighbors, areasoverlengths, conductivities,
+                        sources, dirichletnodes, dirichletheads, metaindex=None, logtransformconductivity=False,
+                        device=0):
+    """int (df/dp)^T lambda dt for p = [conductivities; sources; dirichletheads] (route A of the reference:
+    `dfdp(t) * lambda(t)` of src/transientadjointutils.jl:22-32 integrated as in src/transient.jl:207-209), with
+    f = D^-1 (b - A u).  us/ts: forward states on all N nodes; lambdas/ts_lambda: adjoint states on the free
+    rows (as returned by backwardeulerintegrate / adjointintegrate).  The per-face gather runs on the GPU
+    (fvb_gradient_*); u and lambda are piecewise linear in t, so Simpson on the merged grid is exact."""
+    from .api import _metaindex_table
+    nb = np.asarray(neighbors, np.int64).reshape(-1, 2)
+    F = nb.shape[0]
+    cond = np.asarray(conductivities, np.float64)
+    N, ND = len(sources), len(dirichletheads)
+    sysm = System(device).assemble(nb, areasoverlengths, cond, sources, dirichletnodes, dirichletheads, metaindex,
+                                   logtransformconductivity)
+    try:
+        sysm.set_storage(float(Ss), np.asarray(volumes, np.float64))
+        freenode = sysm.freenode()
+        uc = getcontinuoussolution([np.asarray(u)[freenode] for u in us], ts)
+        lc = getcontinuoussolution(lambdas, ts_lambda)
+        qt, qw = _simpson_nodes([ts, ts_lambda], tspan[0], tspan[1])
+        sysm.gradient_begin(nb)
+        for t, w in zip(qt, qw):
+            sysm.vec_upload(0, uc(t))
+            sysm.vec_upload(1, lc(t))
+            sysm.gradient_accumulate(0, 1, w)
+        gk, gh, slot, gs = sysm.gradient_end(F)
+        meta = _metaindex_table(metaindex, F)
+        idx = np.arange(F) if meta is None else meta - 1
+        out = np.zeros(cond.size + N + ND)
+        out[:cond.size] = np.bincount(idx, weights=gk, minlength=cond.size)            # faces -> conductivity index
+        out[cond.size:cond.size + N][freenode] = gs                                     # free rows -> nodes
+        has = slot > 0
+        out[cond.size + N:] = np.bincount(slot[has] - 1, weights=gh[has], minlength=ND)  # faces -> Dirichlet head
+        return out
+    finally:
+        sysm.close()
+
+
+def gradientintegrate(lambda0, du0dp, integrated_dgdp, integrateddfdplambda_):
+    """src/transient.jl:212-216: dG/dp = du0dp * lambda(0) + int dg/dp dt + int (df/dp)^T lambda dt."""
+    first = 0.0 if du0dp is None else du0dp @ np.asarray(lambda0)
+    return first + integrated_dgdp + integrateddfdplambda_

@@ -119,6 +119,22 @@ int fvb_set_halo_plan(fvb_handle h, int n_peers, const int32_t *peer_ranks,
                       const int64_t *send_counts, const int32_t *send_rows,
                       const int64_t *recv_counts);
 
+/* ---- adjoint gradient (src/transientadjointutils.jl:22-32 `dfdp(t)*lambda`, route A of
+ * gradientintegrate, src/transient.jl:207-216): per-face gather of (df/dp)^T lambda for the ODE
+ * right-hand side f = D^-1 (b - A u), D = Ss*volumes, accumulated over quadrature points.
+ *   face i joining free rows r1,r2, c_i its conductance, dc = c_i (log K) or aol_i (plain K):
+ *       d/dk[metaindex(i)]  +=  w * ( -dc (u1-u2) (l1/D1 - l2/D2) )
+ *   face with r1 free and Dirichlet node d:
+ *       d/dk[metaindex(i)]  +=  w * dc (h_d - u1) l1/D1 ;   d/dh_d += w * c_i l1/D1
+ *   free row r:            d/dsources[node(r)] += w * l_r/D_r
+ * Accumulators are per FACE and per ROW (one writer each: deterministic, no float atomics); the
+ * host folds faces onto conductivity / Dirichlet-head indices in face order.
+ * begin: pass the same neighbors list as fvb_assemble (it is not kept after assembly). */
+int fvb_gradient_begin(fvb_handle h, const int64_t *neighbors);
+int fvb_gradient_accumulate(fvb_handle h, int u_slot, int lambda_slot, double weight);
+int fvb_gradient_end(fvb_handle h, double *grad_cond_face, double *grad_dhead_face, int64_t *dhead_slot_face,
+                     double *grad_source_rows);
+
 /* ---- NVLink peer-memory exchange (optional, same node, after fvb_set_halo_plan) --------------
  * Replaces the per-iteration NCCL calls (halo send/recv, two all-reduces) by kernels that store
  * straight into the neighbours' memory mapped through CUDA IPC.  Every rank calls
