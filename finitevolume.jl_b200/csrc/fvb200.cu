@@ -42,7 +42,9 @@ struct MgState {
   bool ready = false;
   int nlev = 0;
   MgLevel lev[kMgMaxLevels];
-  double *own[kMgMaxLevels][7] = {};  // diag, up0..2, x, r, t owned by level l (level 0 owns only x, t)
+  double *own[kMgMaxLevels][8] = {};  // diag, up0..2, x, r, t, lo_c owned by level l (level 0 owns only x, t)
+  bool dist = false;                  // V-cycle spans the ranks (halo planes exchanged per level)
+  int lo_rank = -1, hi_rank = -1;
 };
 }  // namespace fvb
 
@@ -346,13 +348,27 @@ int mg_setup(fvb_handle h, bool structure) {
     for (auto &lv : M.own) for (auto &p : lv) dfree(h, p);
     M.ready = false;
     M.nlev = 0;
+    M.dist = false;
     if (!h->dia_on || h->dia_K != 3 || h->dia_off[0] != 1) return FVB_OK;
     const int64_t n = h->nf_local, nz = h->dia_off[1], nynz = h->dia_off[2];
     if (nz < 2 || nynz % nz != 0 || n % nynz != 0 || nynz / nz < 2 || n / nynz < 1) return FVB_OK;
     MgLevel &L0 = M.lev[0];
+    L0 = MgLevel{};
     L0.nz = (int)nz; L0.ny = (int)(nynz / nz); L0.nx = (int)(n / nynz); L0.n = n;
     L0.diag = h->diag;
     for (int k = 0; k < 3; ++k) L0.up[k] = h->dia_U[k] + h->dia_off[k];
+    // slab neighbours: exactly one plane of halo columns below and/or above, owned by rank-1 / rank+1
+    if (h->nranks > 1) {
+      const bool lo = h->dia_nlo == nynz && h->rank > 0, hi = h->dia_nhi == nynz && h->rank + 1 < h->nranks;
+      const bool clean = (h->dia_nlo == 0 || lo) && (h->dia_nhi == 0 || hi);
+      if (clean && (lo || hi) && h->comm && h->comm->comm) {
+        M.dist = true;
+        M.lo_rank = lo ? h->rank - 1 : -1;
+        M.hi_rank = hi ? h->rank + 1 : -1;
+        L0.lo_c = lo ? h->dia_U[2] : nullptr;  // U_2[r], r < o_2: lower entries whose partner row is not owned
+        L0.has_hi = hi ? 1 : 0;
+      }
+    }
     int *d_flag = nullptr;
     FVB_TRY(dalloc(h, &d_flag, 1));
     cudaMemsetAsync(d_flag, 0, sizeof(int), st);
@@ -363,36 +379,91 @@ int mg_setup(fvb_handle h, bool structure) {
     dfree(h, d_flag);
     if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
     if (flag) return FVB_OK;
-    FVB_TRY(dalloc(h, &M.own[0][4], n));  // x (= z, the preconditioned residual)
-    FVB_TRY(dalloc(h, &M.own[0][6], n));  // t
+    FVB_TRY(dalloc(h, &M.own[0][4], n + 2 * nynz));  // x (= z, the preconditioned residual) + halo planes
+    FVB_TRY(dalloc(h, &M.own[0][6], n + 2 * nynz));  // t
+    FVB_CUDA(cudaMemsetAsync(M.own[0][4], 0, sizeof(double) * (size_t)(n + 2 * nynz), st));
+    FVB_CUDA(cudaMemsetAsync(M.own[0][6], 0, sizeof(double) * (size_t)(n + 2 * nynz), st));
     L0.x = M.own[0][4]; L0.r = nullptr; L0.t = M.own[0][6];
     int l = 0;
-    while (M.lev[l].n > kMgCoarsest && l + 1 < kMgMaxLevels) {
+    // Stop rule: single GPU -- local size; distributed -- the (y,z) plane only, so that every rank
+    // builds the same number of levels whatever its number of x-planes.
+    auto go_on = [&](const MgLevel &F) {
+      return M.dist ? ((int64_t)F.ny * F.nz > 64 && F.ny >= 2 && F.nz >= 2) : (F.n > kMgCoarsest);
+    };
+    while (go_on(M.lev[l]) && l + 1 < kMgMaxLevels) {
       const MgLevel &F = M.lev[l];
       MgLevel &C = M.lev[l + 1];
+      C = MgLevel{};
       C.nx = (F.nx + 1) / 2; C.ny = (F.ny + 1) / 2; C.nz = (F.nz + 1) / 2;
       C.n = (int64_t)C.nx * C.ny * C.nz;
-      for (int a = 0; a < 7; ++a) FVB_TRY(dalloc(h, &M.own[l + 1][a], C.n));
+      const int64_t pl = (int64_t)C.ny * C.nz;
+      for (int a = 0; a < 4; ++a) FVB_TRY(dalloc(h, &M.own[l + 1][a], C.n));
+      FVB_TRY(dalloc(h, &M.own[l + 1][4], C.n + 2 * pl));
+      FVB_TRY(dalloc(h, &M.own[l + 1][5], C.n));
+      FVB_TRY(dalloc(h, &M.own[l + 1][6], C.n + 2 * pl));
+      FVB_CUDA(cudaMemsetAsync(M.own[l + 1][4], 0, sizeof(double) * (size_t)(C.n + 2 * pl), st));
+      FVB_CUDA(cudaMemsetAsync(M.own[l + 1][6], 0, sizeof(double) * (size_t)(C.n + 2 * pl), st));
+      if (F.lo_c) FVB_TRY(dalloc(h, &M.own[l + 1][7], pl));
       C.diag = M.own[l + 1][0];
       for (int k = 0; k < 3; ++k) C.up[k] = M.own[l + 1][1 + k];
       C.x = M.own[l + 1][4]; C.r = M.own[l + 1][5]; C.t = M.own[l + 1][6];
+      C.lo_c = F.lo_c ? M.own[l + 1][7] : nullptr;
+      C.has_hi = F.has_hi;
       ++l;
     }
     M.nlev = l + 1;
+  }
+  if (structure && h->nranks > 1 && h->comm && h->comm->comm) {
+    // All ranks must take the same path through the solver (its collectives are matched call by
+    // call): agree on the weakest capability -- 0 none, 1 block-local V-cycle, 2 distributed.
+    int mine = M.nlev == 0 ? 0 : (M.dist ? 2 : 1), all = 0;
+    int *d_v = nullptr;
+    FVB_TRY(dalloc(h, &d_v, 1));
+    FVB_CUDA(cudaMemcpyAsync(d_v, &mine, sizeof(int), cudaMemcpyHostToDevice, st));
+    FVB_NCCL(nccl().AllReduce(d_v, d_v, 1, ncclInt, ncclMin, h->comm->comm, st));
+    cudaError_t e = memcpy_sync(st, &all, d_v, sizeof(int), cudaMemcpyDeviceToHost);
+    dfree(h, d_v);
+    if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+    if (all == 0) { M.nlev = 0; return FVB_OK; }
+    if (all == 1 && M.dist) {
+      // somebody cannot exchange planes: everybody preconditions with its own diagonal block
+      M.dist = false;
+      for (int l = 0; l < M.nlev; ++l) { M.lev[l].lo_c = nullptr; M.lev[l].has_hi = 0; }
+    }
   }
   if (M.nlev == 0) return FVB_OK;
   for (int l = 0; l + 1 < M.nlev; ++l) {
     const MgLevel &C = M.lev[l + 1];
     k_mg_coarsen<<<grid_for(C.n), kBlock, 0, st>>>(M.lev[l], C.nx, C.ny, C.nz, M.own[l + 1][0], M.own[l + 1][1],
-                                                   M.own[l + 1][2], M.own[l + 1][3]);
+                                                   M.own[l + 1][2], M.own[l + 1][3], M.own[l + 1][7]);
     h->tm.kernel_launches++;
   }
   M.ready = true;
   return FVB_OK;
 }
 
+// Exchange the boundary planes of one level's iterate with the slab neighbours (NCCL; the planes are
+// contiguous: first/last ny*nz entries out, halo slots [n, n+pl) and [n+pl, n+2pl) in).
+int mg_halo(fvb_handle h, const MgLevel &L, double *v) {
+  MgState &M = *h->mg;
+  if (!M.dist) return FVB_OK;
+  const size_t pl = (size_t)L.ny * L.nz;
+  NcclApi &N = nccl();
+  FVB_NCCL(N.GroupStart());
+  if (M.lo_rank >= 0) {
+    FVB_NCCL(N.Send(v, pl, ncclDouble, M.lo_rank, h->comm->comm, h->stream));
+    FVB_NCCL(N.Recv(v + L.n, pl, ncclDouble, M.lo_rank, h->comm->comm, h->stream));
+  }
+  if (M.hi_rank >= 0) {
+    FVB_NCCL(N.Send(v + L.n - pl, pl, ncclDouble, M.hi_rank, h->comm->comm, h->stream));
+    FVB_NCCL(N.Recv(v + L.n + pl, pl, ncclDouble, M.hi_rank, h->comm->comm, h->stream));
+  }
+  FVB_NCCL(N.GroupEnd());
+  return FVB_OK;
+}
+
 // z = M^-1 r : one V-cycle.  r is only read; the result lands in lev[0].x.
-void mg_vcycle(fvb_handle h, const double *r) {
+int mg_vcycle(fvb_handle h, const double *r) {
   MgState &M = *h->mg;
   cudaStream_t st = h->stream;
   const int nu = h->mg_nu;
@@ -404,30 +475,53 @@ void mg_vcycle(fvb_handle h, const double *r) {
     const int g = mg_grid(h, L.n);
     double *cur = L.t, *oth = L.x;  // 2*nu-1 swaps in total: start in t to finish in x
     k_mg_smooth0<<<g, kBlock, 0, st>>>(L, L.r, cur, om, h->scal);
-    for (int s = 1; s < nu; ++s) { k_mg_smooth<<<g, kBlock, 0, st>>>(L, L.r, cur, oth, om, h->scal); std::swap(cur, oth); }
+    for (int s = 1; s < nu; ++s) {
+      FVB_TRY(mg_halo(h, L, cur));
+      k_mg_smooth<<<g, kBlock, 0, st>>>(L, L.r, cur, oth, om, h->scal);
+      std::swap(cur, oth);
+    }
     const MgLevel &C = M.lev[l + 1];
+    FVB_TRY(mg_halo(h, L, cur));
     k_mg_restrict<<<mg_grid(h, C.n), kBlock, 0, st>>>(L, L.r, cur, C.nx, C.ny, C.nz, C.r, h->scal);
     h->tm.kernel_launches += nu + 1;
   }
   {
     MgLevel &L = M.lev[M.nlev - 1];
-    // (with a single level the matrix is tiny and the sweeps are the whole preconditioner)
-    k_mg_coarse_solve<<<1, kBlock, 0, st>>>(L, L.r, L.x, L.t, om, kMgCoarseSweeps, h->scal);
-    h->tm.kernel_launches++;
+    if (!M.dist) {
+      // (with a single level the matrix is tiny and the sweeps are the whole preconditioner)
+      k_mg_coarse_solve<<<1, kBlock, 0, st>>>(L, L.r, L.x, L.t, om, kMgCoarseSweeps, h->scal);
+      h->tm.kernel_launches++;
+    } else {
+      // the coarsest problem is spread over the ranks: the same fixed number of sweeps, planes exchanged
+      const int g = mg_grid(h, L.n);
+      double *cur = L.t, *oth = L.x;  // kMgCoarseSweeps is even: an odd number of swaps ends in x
+      k_mg_smooth0<<<g, kBlock, 0, st>>>(L, L.r, cur, om, h->scal);
+      for (int s = 1; s < kMgCoarseSweeps; ++s) {
+        FVB_TRY(mg_halo(h, L, cur));
+        k_mg_smooth<<<g, kBlock, 0, st>>>(L, L.r, cur, oth, om, h->scal);
+        std::swap(cur, oth);
+      }
+      h->tm.kernel_launches += kMgCoarseSweeps;
+    }
   }
   // going up
   for (int l = M.nlev - 2; l >= 0; --l) {
     MgLevel &L = M.lev[l];
     const int g = mg_grid(h, L.n);
     const MgLevel &C = M.lev[l + 1];
-    // where the pre-smoothed iterate lives: t after an odd number (nu-1 even -> t, odd -> x) of swaps
+    // where the pre-smoothed iterate lives: t after an even number of swaps, x after an odd one
     double *cur = ((nu - 1) % 2 == 0) ? L.t : L.x;
     double *oth = cur == L.t ? L.x : L.t;
     k_mg_prolong<<<g, kBlock, 0, st>>>(L, C.ny, C.nz, C.x, cur, oc, h->scal);
-    for (int s = 0; s < nu; ++s) { k_mg_smooth<<<g, kBlock, 0, st>>>(L, L.r, cur, oth, om, h->scal); std::swap(cur, oth); }
+    for (int s = 0; s < nu; ++s) {
+      FVB_TRY(mg_halo(h, L, cur));
+      k_mg_smooth<<<g, kBlock, 0, st>>>(L, L.r, cur, oth, om, h->scal);
+      std::swap(cur, oth);
+    }
     h->tm.kernel_launches += nu + 1;
     // cur == L.x by construction
   }
+  return FVB_OK;
 }
 
 // CG preconditioned by the V-cycle, steady operator only.  x0 (if any) already in h->x.
@@ -535,7 +629,7 @@ int pcg_mg_run(fvb_handle h, const double *rhs, bool have_x0, double rtol, int64
   while (!stop) {
     int64_t todo = std::min<int64_t>(batch, maxiter - enq);
     for (int64_t it = 0; it < todo; ++it) {
-      mg_vcycle(h, h->r);
+      FVB_TRY(mg_vcycle(h, h->r));
       const double *z = M.lev[0].x;
       k_mgpcg_rz<<<vg, kBlock, 0, st>>>(n, h->r, z, h->partials, h->ticket, h->scal, fin);
       h->tm.kernel_launches++;

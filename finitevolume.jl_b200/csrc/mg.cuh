@@ -16,9 +16,15 @@
 //     smooth error -- measured 38 -> 20 PCG iterations at 128^3 with oc = 1.5);
 //   * the coarsest level (<= kMgCoarsest unknowns) is "solved" by a fixed number of sweeps in one CTA.
 // Levels store only upper couplings up_k[r] = A[r, r+o_k] (the lower one is up_k[r-o_k]).  On level 0
-// they alias the handle's diagonal copy; couplings that leave the local box (slab halos in
-// multi-GPU runs) are dropped by range checks, i.e. each rank preconditions with the multigrid of
-// its own diagonal block (non-overlapping additive Schwarz) and no V-cycle traffic crosses NVLink.
+// they alias the handle's diagonal copy.
+// Multi-GPU (x-slabs): aggregates never straddle ranks, so every level is again slab-partitioned with
+// the same (y,z) plane on all ranks.  The iterate buffers carry one halo plane per side
+// ([owned n | plane from the rank below | plane from the rank above]); the coupling of a first-plane
+// row to the rank below is lo_c[r] (level 0: the diagonal copy's prefix; coarser: sum over the
+// children, k_mg_coarsen), the coupling of a last-plane row to the rank above is its up[2][r].  The
+// host exchanges the boundary planes before every operator application (4 per level and V-cycle at
+// nu = 2), so the distributed V-cycle is the same operator as the single-GPU one up to the
+// rank-aligned aggregate boundaries and the inexact coarsest solve.
 #pragma once
 #include "common.cuh"
 #include "reduce.cuh"
@@ -27,7 +33,7 @@ namespace fvb {
 
 constexpr int kMgMaxLevels = 12;
 constexpr int kMgCoarsest = 256;     // stop coarsening at or below this many unknowns
-constexpr int kMgCoarseSweeps = 24;  // damped-Jacobi sweeps on the coarsest level (fixed => linear operator)
+constexpr int kMgCoarseSweeps = 24;  // damped-Jacobi sweeps on the coarsest level (fixed => linear operator; even)
 constexpr int kMgCtasPerSm = 4;
 
 struct MgLevel {
@@ -35,7 +41,9 @@ struct MgLevel {
   int64_t n;
   const double *diag;    // [n]
   const double *up[3];   // up[k][r] = A[r, r + o_k], o = (1, nz, ny*nz); may be read at r - o_k >= 0
-  double *x, *r, *t;     // correction, right-hand side, scratch (ping-pong for Jacobi)
+  double *x, *r, *t;     // correction, right-hand side, scratch (ping-pong for Jacobi); x,t: n + 2*ny*nz
+  const double *lo_c;    // [ny*nz] couplings of the first plane to the rank below, or null
+  int has_hi;            // the last plane's up[2] couples to the rank above (halo at v[n + ny*nz + j])
 };
 
 // (A v)[r] for the level's stencil, neighbours outside [0,n) skipped
@@ -47,7 +55,9 @@ __device__ __forceinline__ double mg_apply(const MgLevel &L, const double *__res
   if (r >= o1) acc += L.up[1][r - o1] * v[r - o1];
   if (r + o1 < L.n) acc += L.up[1][r] * v[r + o1];
   if (r >= o2) acc += L.up[2][r - o2] * v[r - o2];
+  else if (L.lo_c) acc += L.lo_c[r] * v[L.n + r];                       // plane of the rank below
   if (r + o2 < L.n) acc += L.up[2][r] * v[r + o2];
+  else if (L.has_hi) acc += L.up[2][r] * v[L.n + o2 + (r - (L.n - o2))];  // plane of the rank above
   return acc;
 }
 
@@ -115,9 +125,8 @@ k_mg_prolong(MgLevel L, int cy, int cz, const double *__restrict__ ec, double *_
 // Galerkin coarse operator of one level (fine level Lf -> arrays of the next level)
 __global__ void __launch_bounds__(kBlock)
 k_mg_coarsen(MgLevel Lf, int cx, int cy, int cz, double *__restrict__ dc, double *__restrict__ u0,
-             double *__restrict__ u1, double *__restrict__ u2) {
+             double *__restrict__ u1, double *__restrict__ u2, double *__restrict__ lo_c_coarse) {
   const int64_t nc = (int64_t)cx * cy * cz;
-  const int64_t o1 = Lf.nz, o2 = (int64_t)Lf.ny * Lf.nz;
   for (int64_t I = (int64_t)blockIdx.x * kBlock + threadIdx.x; I < nc; I += (int64_t)gridDim.x * kBlock) {
     const int Iz = (int)(I % cz), Iy = (int)((I / cz) % cy), Ix = (int)(I / ((int64_t)cz * cy));
     double d = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
@@ -131,13 +140,23 @@ k_mg_coarsen(MgLevel Lf, int cx, int cy, int cz, double *__restrict__ dc, double
           // +z, +y, +x couplings of the child; couplings leaving the local box are not part of it
           const double cz_ = (iz + 1 < Lf.nz) ? Lf.up[0][r] : 0.0;
           const double cy_ = (iy + 1 < Lf.ny) ? Lf.up[1][r] : 0.0;
-          const double cx_ = (ix + 1 < Lf.nx && r + o2 < Lf.n) ? Lf.up[2][r] : 0.0;
-          (void)o1;
+          // the +x coupling of the last plane leaves the box: kept only when a rank above exists
+          const double cx_ = (ix + 1 < Lf.nx) ? Lf.up[2][r] : (Lf.has_hi ? Lf.up[2][r] : 0.0);
           if (dz == 0 && iz + 1 < Lf.nz) d += 2.0 * cz_; else a0 += cz_;
           if (dy == 0 && iy + 1 < Lf.ny) d += 2.0 * cy_; else a1 += cy_;
           if (dx == 0 && ix + 1 < Lf.nx) d += 2.0 * cx_; else a2 += cx_;
         }
     dc[I] = d; u0[I] = a0; u1[I] = a1; u2[I] = a2;
+    if (lo_c_coarse && Ix == 0) {
+      // coupling of the first coarse plane to the rank below = sum over its children in fine plane 0
+      double lc = 0.0;
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dz = 0; dz < 2; ++dz) {
+          const int iy = 2 * Iy + dy, iz = 2 * Iz + dz;
+          if (iy < Lf.ny && iz < Lf.nz) lc += Lf.lo_c[(int64_t)iy * Lf.nz + iz];
+        }
+      lo_c_coarse[(int64_t)Iy * cz + Iz] = lc;
+    }
   }
 }
 

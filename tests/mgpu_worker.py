@@ -78,8 +78,9 @@ def main():
         dn_ref = np.linalg.norm(sg - 0.5)
         hmg = np.concatenate([o[7] for o in out])
         err_mg = np.max(np.abs(hmg - ho)) / np.max(np.abs(ho))
+        # distributed V-cycle: iteration count must stay in the single-GPU class, far below Jacobi
         mg_ok = (err_mg <= 1e-8 and all(o[9] for o in out) and len({o[8] for o in out}) == 1
-                 and all(o[10] == "mg" for o in out) and out[0][8] < out[0][2])
+                 and all(o[10] == "mg" for o in out) and out[0][8] * 3 < out[0][2])
         iters = {o[2] for o in out}
         ok = (err_h <= 1e-8 and err_y <= 1e-12 and err_s <= 1e-8 and len(iters) == 1 and all(o[3] for o in out)
               and abs(out[0][5] - dn_ref) <= 1e-10 * dn_ref and all(o[6] for o in out)
