@@ -358,6 +358,7 @@ def main():
     barrier()
     wall = time.perf_counter() - w0
     launches = sysm.timings()["kernel_launches"] - l0
+    scaled = sysm.pcg_scaling()  # the timed solves ran the symmetrically scaled recurrence (unit-diagonal SpMV)
     clocks = sampler.stop()
     last_tm = sysm.timings()
     sz = sysm.sizes()
@@ -365,6 +366,9 @@ def main():
     wall_s = maxreduce(wall / args.steps)
 
     # ---- timed: end to end from pinned host buffers -------------------------------------------
+    # (one untimed pass first: the host-pointer call stages its inputs in device buffers the
+    # device-resident passes above never allocated, and growing the memory pool is a one-off cost)
+    step(host_ptrs, head_host.data_ptr())
     barrier()
     e0 = time.perf_counter()
     for _ in range(max(args.e2e_steps, 1)):
@@ -431,7 +435,8 @@ def main():
     csr_bytes = spmv_bytes(sz["nf_local"], sz["nnz_local"])
     # an index-free diagonal format is reported against ITS algorithmic bytes
     # (8 per stored diagonal entry incl. the main diagonal, x read once, y written once)
-    alg_bytes = (8 * (fmt_k + 1) + 16) * sz["nf_local"] if fmt == "dia" else csr_bytes
+    # (the scaled copy has a unit diagonal that is not stored: 8 bytes per row fewer)
+    alg_bytes = (8 * (fmt_k + (0 if scaled else 1)) + 16) * sz["nf_local"] if fmt == "dia" else csr_bytes
     achieved = alg_bytes / (spmv_avg_ms * 1e-3) / 1e9 if spmv_samples else None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -445,7 +450,8 @@ def main():
         try:
             tj = json.load(open(tpath))
             if tj.get("grid_n") == n and world == 1:
-                traffic = tj.get(fmt)  # per launch, from the committed ncu --set full capture
+                # per launch, from the committed ncu --set full capture
+                traffic = tj.get("dia_scaled" if (fmt == "dia" and scaled) else fmt)
         except Exception:
             pass
 
@@ -481,7 +487,9 @@ def main():
             "e2e_device_grid": devgrid,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm",
-                         "kernel": ("k_spmv_dia<true,%d> (symmetric-diagonal SpMV + fused u.Au)" % fmt_k) if fmt == "dia"
+                         "kernel": ("k_spmv_dia<true,%d,%s> (symmetric-diagonal SpMV%s + fused u.Au)"
+                                    % (fmt_k, "true" if scaled else "false",
+                                       " on the Jacobi-scaled unit-diagonal copy" if scaled else "")) if fmt == "dia"
                          else "k_spmv<true> (CSR SpMV + fused u.Au)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
@@ -490,7 +498,9 @@ def main():
                          "csr_kernel": csr_roof,
                          "note": "rank-local rows; min over ranks" if world > 1 else "sampled inside the timed solves"},
             "cpu_baseline": cpu,
-            "precond": args.precond, "alt_precond": alt_info,
+            "precond": args.precond, "pcg_scaled": bool(scaled),
+            "pcg_bytes_per_row_per_iteration": (112 if scaled else 128) if fmt == "dia" else None,
+            "alt_precond": alt_info,
             "pcg_iterations": it, "converged": bool(conv), "result_sane": ok,
             "assemble_ms": last_tm["assemble_ms"], "solve_ms": last_tm["solve_ms"],
             "wall_s_per_step": wall_s, "input_generation_s": t_gen,

@@ -370,14 +370,32 @@ class System:
         return ("mg" if a.value == 1 else "jacobi"), l.value
 
     def set_spmv_format(self, fmt):
-        """0 = automatic (diagonal copy when the pattern allows), 1 = always CSR."""
+        """0 = automatic (diagonal copy when the pattern allows), 1 = always CSR, 2 = diagonal copy with the
+        per-thread-load kernel only, 3 = diagonal copy through the TMA pipeline whatever the size."""
         check(lib().fvb_set_spmv_format(self._h, C.c_int(int(fmt))))
 
     def spmv_format(self):
         """-> ("csr" | "dia", number of positive offsets)."""
         a, k = C.c_int(), C.c_int()
         check(lib().fvb_get_spmv_format(self._h, C.byref(a), C.byref(k)))
-        return ("dia" if a.value == 2 else "csr"), k.value
+        return ("dia" if a.value in (2, 3) else "csr"), k.value
+
+    def spmv_kernel(self):
+        """-> "csr" | "dia" (per-thread loads) | "dia_tma" (TMA pipeline): the kernel the next product uses."""
+        a, k = C.c_int(), C.c_int()
+        check(lib().fvb_get_spmv_format(self._h, C.byref(a), C.byref(k)))
+        return {1: "csr", 2: "dia", 3: "dia_tma"}[a.value]
+
+    def set_pcg_scaling(self, mode):
+        """0 = automatic (cold-started steady Jacobi solves on the diagonal format run the symmetrically
+        scaled recurrence, include/fvb200.h), 1 = never."""
+        check(lib().fvb_set_pcg_scaling(self._h, C.c_int(int(mode))))
+
+    def pcg_scaling(self):
+        """-> True when the last solve on this system ran the scaled recurrence."""
+        a = C.c_int()
+        check(lib().fvb_get_pcg_scaling(self._h, C.byref(a)))
+        return bool(a.value)
 
     def set_profiling(self, stride):
         check(lib().fvb_set_profiling(self._h, C.c_int(int(stride))))

@@ -107,12 +107,20 @@ struct fvb_handle_s {
   int64_t u_cap = 0;               // capacity of u (plain cudaMalloc when nranks > 1: IPC-exportable)
 
   // index-free diagonal copy of A (dia.cuh), built when the pattern allows
-  int fmt_request = 0;          // 0 auto, 1 CSR only
+  int fmt_request = 0;          // 0 auto, 1 CSR only, 2 diagonal with per-thread loads only, 3 diagonal TMA forced
+  bool last_dia_tma = false;    // the last diagonal SpMV launch used the TMA pipeline (dia_tma.cuh)
   bool dia_on = false;
   int dia_K = 0;
   int64_t dia_off[4] = {};
   double *dia_U[4] = {};
   int64_t dia_lo0 = 0, dia_nlo = 0, dia_hi0 = 0, dia_nhi = 0;
+
+  // symmetric Jacobi scaling of that copy (dia.cuh: k_dia_scale; pcg.cuh: SC kernels)
+  int scale_request = 0;        // 0 auto, 1 never
+  int scale_state = 0;          // 0 not built for the current values, 1 ready, 2 not applicable
+  double *dia_S[4] = {};        // D^-1/2 U_k D^-1/2, same layout as dia_U
+  double *sinv = nullptr;       // [nf_local] diag^-1/2
+  bool last_solve_scaled = false;
 
   // adjoint gradient accumulators (fvb_gradient_*)
   int logk = 0;

@@ -16,8 +16,14 @@
 // halo runs).  Absent entries are stored as 0 and skipped, so no out-of-range x is ever read.
 //
 // Row sums run in ascending column order with separate multiply/add, like the CSR kernel.
+//
+// UNIT variant (symmetric Jacobi scaling): for the steady Jacobi-PCG the solver keeps a second copy
+// S_k of the diagonals holding A^ = D^-1/2 A D^-1/2 (k_dia_scale).  A^ has a unit diagonal, so the
+// kernel streams no diag array (8*K+16 bytes per row, 40 at K = 3) and CG on A^ needs no
+// preconditioner reads at all -- see pcg.cuh.
 #pragma once
 #include "common.cuh"
+#include "peer_base.cuh"
 #include "reduce.cuh"
 
 namespace fvb {
@@ -82,6 +88,51 @@ __global__ void k_dia_fill(int nrows, const int *__restrict__ rowptr, const int 
   }
 }
 
+// ---- symmetric Jacobi scaling: S = D^-1/2 U D^-1/2 -------------------------------------------------
+// s[r] = diag[r]^-1/2 into the solver's vector layout [owned rows | halo slots] (the halo slots are
+// filled by the ordinary halo exchange afterwards) and into sinv.  flag[0] = 1 when some diagonal
+// entry is not a positive finite number (the scaling -- like the Jacobi preconditioner -- needs one).
+__global__ void k_make_sinv(int64_t n, const double *__restrict__ diag, double *__restrict__ s_vec,
+                            double *__restrict__ sinv, int *__restrict__ flag) {
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double d = diag[i];
+    const bool ok = d > 0.0 && d <= 1.79769313486231570e308;
+    bad |= !ok;
+    const double s = ok ? 1.0 / sqrt(d) : 1.0;
+    s_vec[i] = s;
+    sinv[i] = s;
+  }
+  if (bad) *flag = 1;
+}
+
+// S_k[j] = U_k[j] * (s[row] * s[col]).  The factor is a commutative product, so the copy stays
+// exactly symmetric and the two ranks that share a cut face compute the same bits.
+template <int K>
+__global__ void __launch_bounds__(kBlock)
+k_dia_scale(int nrows, DiaDesc D, const double *__restrict__ s, double *S0, double *S1, double *S2, double *S3) {
+  double *const S[4] = {S0, S1, S2, S3};
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    const double sr = s[r];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int64_t o = D.off[k];
+      double up = D.U[k][o + r];  // A[r, r+o]
+      if (up != 0.0) {
+        const int64_t iu = r + o;
+        const double sc = s[iu < D.nf ? iu : D.xindex(D.row_start + iu)];
+        up = __dmul_rn(up, __dmul_rn(sr, sc));
+      }
+      S[k][o + r] = up;
+      if (r < o) {                // A[r, r-o], partner row owned by the rank below (or absent)
+        double lo = D.U[k][r];
+        if (lo != 0.0) lo = __dmul_rn(lo, __dmul_rn(sr, s[D.xindex(D.row_start + r - o)]));
+        S[k][r] = lo;
+      }
+    }
+  }
+}
+
 // ---- the SpMV ------------------------------------------------------------------------------------------
 constexpr int kDiaRowsPerThread = 2;
 
@@ -89,11 +140,11 @@ constexpr int kDiaCtasPerSm = 3;  // the grid must be fully resident: the grid-s
                                   // moving front a fraction of a plane thick, and the plane-distance
                                   // re-reads (lower diagonals, x[r +- n2*n3]) hit L2 instead of HBM
 
-template <bool DOT, int K>
+template <bool DOT, int K, bool UNIT>
 __global__ void __launch_bounds__(kBlock, kDiaCtasPerSm)
 k_spmv_dia(int nrows, DiaDesc D, const double *__restrict__ x, double *__restrict__ y,
            const double *__restrict__ Dvec, double sigma, double *__restrict__ partials, unsigned int *ticket,
-           PcgScal *scal, int finalize_mode) {
+           PcgScal *scal, int finalize_mode, PeerRed pr) {
   if (DOT && scal->done) return;
   constexpr int R = kDiaRowsPerThread;
   double dot = 0.0;
@@ -105,7 +156,7 @@ k_spmv_dia(int nrows, DiaDesc D, const double *__restrict__ x, double *__restric
     for (int j = 0; j < R; ++j) {
       const int64_t r = base + j * kBlock + threadIdx.x;
       if (r < nrows) {
-        dg[j] = __ldg(&D.diag[r]);
+        dg[j] = UNIT ? 1.0 : __ldg(&D.diag[r]);
         xr[j] = x[r];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -127,11 +178,11 @@ k_spmv_dia(int nrows, DiaDesc D, const double *__restrict__ x, double *__restric
 #pragma unroll
         for (int k = K - 1; k >= 0; --k)  // most negative column first
           if (lo[j][k] != 0.0) acc = __dadd_rn(acc, __dmul_rn(lo[j][k], xl[j][k]));
-        acc = __dadd_rn(acc, __dmul_rn(dg[j], xr[j]));
+        acc = __dadd_rn(acc, UNIT ? xr[j] : __dmul_rn(dg[j], xr[j]));
 #pragma unroll
         for (int k = 0; k < K; ++k)
           if (up[j][k] != 0.0) acc = __dadd_rn(acc, __dmul_rn(up[j][k], xu[j][k]));
-        if (sigma != 0.0) acc += sigma * (Dvec ? Dvec[r] : 1.0) * xr[j];
+        if (!UNIT && sigma != 0.0) acc += sigma * (Dvec ? Dvec[r] : 1.0) * xr[j];
         y[r] = acc;
         dot += xr[j] * acc;
       }
@@ -140,8 +191,9 @@ k_spmv_dia(int nrows, DiaDesc D, const double *__restrict__ x, double *__restric
   if (DOT) {
     double s = block_sum(dot);
     if (last_block_sum1(s, partials, ticket, &s)) {
+      const bool ok = finalize_mode != 2 || peer_allreduce_thread(pr, &s, 1, scal);
       scal->red[0] = s;
-      if (finalize_mode == 1) scal->uc = s;
+      if (ok && finalize_mode >= 1) scal->uc = s;
     }
   }
 }

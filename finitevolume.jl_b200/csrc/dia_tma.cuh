@@ -1,0 +1,263 @@
+// dia_tma.cuh -- the symmetric-diagonal SpMV of dia.cuh as a persistent, warp-specialised
+// TMA pipeline (same structure as the CSR kernel in spmv.cuh).
+//
+// On the diagonal format every operand of a tile of T consecutive rows is a CONTIGUOUS slice:
+//     U_k[o_k + r0 .. +T)  upper entries          U_k[r0 .. +T)   lower entries
+//     x[r0 +- o_k .. +T)   neighbour values       x[r0 .. +T), diag[r0 .. +T)
+// so one elected producer lane can ask the TMA unit (cp.async.bulk -> UBLKCP) for all of them and
+// the eight consumer warps only ever touch shared memory: no LSU/L1 wavefronts, no address
+// arithmetic and no registers are spent on the streams, and two tiles per CTA (four per SM) are
+// in flight regardless of occupancy.  The plane-distance re-reads (lower diagonals, x[r +- n2*n3])
+// are served by L2 exactly as in k_spmv_dia: the grid is resident (2 CTAs/SM) and tiles are dealt
+// round-robin, so the sweep is a moving front thinner than one plane.
+//
+// Offsets o_k <= kDiaNear (the z-neighbour, o = 1) are served from the centre slices, which are
+// fetched with a margin; larger offsets get their own slices, started one element early when o_k is
+// odd so that every copy stays 16-byte aligned.
+//
+// Tiles whose slices would leave the owned range [0, nf) -- the first and last plane of a slab,
+// where columns live in the halo or do not exist -- are "edge" tiles: the producer completes the
+// barrier without copying and the consumers take the per-row path of dia.cuh.  The host only
+// picks this kernel when edge tiles are a small minority (fvb200.cu: launch_spmv).
+//
+// Row sums use the same order and the same separate multiply/add as k_spmv_dia and k_spmv, so
+// y is bit-identical to both.
+#pragma once
+#include "dia.cuh"
+#include "tma.cuh"
+
+namespace fvb {
+
+constexpr int kDiaTmaRows = 256;                        // consumer threads per CTA
+constexpr int kDiaTmaR = 2;                             // rows per consumer thread and tile
+constexpr int kDiaTmaTile = kDiaTmaRows * kDiaTmaR;     // T
+constexpr int kDiaTmaThreads = kDiaTmaRows + 32;        // + producer warp
+constexpr int kDiaTmaStages = 2;
+constexpr int kDiaTmaCtasPerSm = 2;
+constexpr int kDiaNear = 8;                             // margin of the centre slices (even)
+
+// Per-stage layout in doubles (filled on the host: dia_tma_layout).
+struct DiaTmaLayout {
+  int xc;            // x[r0 - kDiaNear .. r0 + T + kDiaNear)
+  int dg;            // diag[r0 .. r0 + T)                                  (unused when UNIT)
+  int un[kDiaMaxOff];  // near k: U_k[r0 .. r0 + T + kDiaNear)
+  int xl[kDiaMaxOff];  // far k:  x[(r0 - o_k) & ~1 .. + T + 2)
+  int xu[kDiaMaxOff];  // far k:  x[(r0 + o_k) & ~1 .. + T + 2)
+  int ul[kDiaMaxOff];  // far k:  U_k[r0 .. r0 + T)
+  int uu[kDiaMaxOff];  // far k:  U_k[(o_k + r0) & ~1 .. + T + 2)
+  int stage_doubles; // size of one stage
+  int bar_off;       // byte offset of the mbarriers / reduction scratch behind the stages
+  uint32_t tx_bytes; // bytes one interior tile brings in
+  int64_t reach;     // interior tiles satisfy r0 >= reach and r0 + T + reach <= nf
+};
+
+inline DiaTmaLayout dia_tma_layout(int K, const int64_t *off, bool unit) {
+  DiaTmaLayout L = {};
+  const int T = kDiaTmaTile;
+  int p = 0, n = 0;
+  auto take = [&](int len) { int at = p; p += len; n += len; return at; };
+  L.xc = take(T + 2 * kDiaNear);
+  if (!unit) L.dg = take(T);
+  int64_t reach = kDiaNear;
+  for (int k = 0; k < K; ++k) {
+    if (off[k] <= kDiaNear) {
+      L.un[k] = take(T + kDiaNear);
+    } else {
+      L.xl[k] = take(T + 2);
+      L.xu[k] = take(T + 2);
+      L.ul[k] = take(T);
+      L.uu[k] = take(T + 2);
+      reach = std::max<int64_t>(reach, off[k] + 2);
+    }
+  }
+  L.stage_doubles = p;
+  L.tx_bytes = (uint32_t)n * 8u;
+  L.bar_off = kDiaTmaStages * p * 8;
+  L.reach = reach;
+  return L;
+}
+inline size_t dia_tma_smem_bytes(const DiaTmaLayout &L) {
+  return (size_t)L.bar_off + 2 * kDiaTmaStages * sizeof(uint64_t) + (kDiaTmaRows / 32) * sizeof(double) + 16;
+}
+
+__device__ __forceinline__ void dia_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kDiaTmaRows) : "memory"); }
+
+// one row straight from global memory (edge tiles): identical arithmetic to k_spmv_dia
+template <int K, bool UNIT>
+__device__ __forceinline__ double dia_row_direct(const DiaDesc &D, const double *__restrict__ x, int64_t r, double xr) {
+  double acc = 0.0;
+#pragma unroll
+  for (int k = K - 1; k >= 0; --k) {
+    const double lo = __ldg(&D.U[k][r]);
+    if (lo != 0.0) {
+      const int64_t il = r - D.off[k];
+      const double xv = il >= 0 ? __ldg(&x[il]) : __ldg(&x[D.xindex(D.row_start + il)]);
+      acc = __dadd_rn(acc, __dmul_rn(lo, xv));
+    }
+  }
+  acc = __dadd_rn(acc, UNIT ? xr : __dmul_rn(__ldg(&D.diag[r]), xr));
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double up = __ldg(&D.U[k][D.off[k] + r]);
+    if (up != 0.0) {
+      const int64_t iu = r + D.off[k];
+      const double xv = iu < D.nf ? __ldg(&x[iu]) : __ldg(&x[D.xindex(D.row_start + iu)]);
+      acc = __dadd_rn(acc, __dmul_rn(up, xv));
+    }
+  }
+  return acc;
+}
+
+template <bool DOT, int K, bool UNIT>
+__global__ void __launch_bounds__(kDiaTmaThreads, kDiaTmaCtasPerSm)
+k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ x, double *__restrict__ y,
+               const double *__restrict__ Dvec, double sigma, double *__restrict__ partials, unsigned int *ticket,
+               PcgScal *scal, int finalize_mode, PeerRed pr) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (DOT && scal->done) return;
+  constexpr int T = kDiaTmaTile;
+  double *const stage0 = reinterpret_cast<double *>(smem_raw);
+  uint64_t *const full = reinterpret_cast<uint64_t *>(smem_raw + L.bar_off);
+  uint64_t *const empty = full + kDiaTmaStages;
+  double *const wsum = reinterpret_cast<double *>(empty + kDiaTmaStages);
+  int *const is_last = reinterpret_cast<int *>(wsum + kDiaTmaRows / 32);
+  const int t = threadIdx.x;
+  const int ntiles = (nrows + T - 1) / T;
+  if (t == 0) {
+    for (int s = 0; s < kDiaTmaStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kDiaTmaRows / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (t >= kDiaTmaRows) {
+    // ---------------- producer warp: one elected lane drives the TMA unit ----------------
+    if (t == kDiaTmaRows) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int stage = it % kDiaTmaStages;
+        if (it >= kDiaTmaStages) mbar_wait(&empty[stage], (uint32_t)((it / kDiaTmaStages - 1) & 1));
+        const int64_t r0 = (int64_t)tile * T;
+        const bool interior = r0 >= L.reach && r0 + T + L.reach <= (int64_t)nrows;
+        if (!interior) {
+          mbar_expect_tx(&full[stage], 0u);  // nothing to copy: the consumers read global memory
+          continue;
+        }
+        double *const sm = stage0 + (size_t)stage * L.stage_doubles;
+        mbar_expect_tx(&full[stage], L.tx_bytes);
+        bulk_g2s(sm + L.xc, x + (r0 - kDiaNear), (T + 2 * kDiaNear) * 8u, &full[stage]);
+        if (!UNIT) bulk_g2s(sm + L.dg, D.diag + r0, T * 8u, &full[stage]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int64_t o = D.off[k];
+          if (o <= kDiaNear) {
+            bulk_g2s(sm + L.un[k], D.U[k] + r0, (T + kDiaNear) * 8u, &full[stage]);
+          } else {
+            const int64_t sh = o & 1;
+            bulk_g2s(sm + L.xl[k], x + (r0 - o - sh), (T + 2) * 8u, &full[stage]);
+            bulk_g2s(sm + L.xu[k], x + (r0 + o - sh), (T + 2) * 8u, &full[stage]);
+            bulk_g2s(sm + L.ul[k], D.U[k] + r0, T * 8u, &full[stage]);
+            bulk_g2s(sm + L.uu[k], D.U[k] + (r0 + o - sh), (T + 2) * 8u, &full[stage]);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers: thread t owns rows r0 + t, r0 + 256 + t of every tile ----------------
+  double dot = 0.0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stage = it % kDiaTmaStages;
+    const int64_t r0 = (int64_t)tile * T;
+    const bool interior = r0 >= L.reach && r0 + T + L.reach <= (int64_t)nrows;
+    mbar_wait(&full[stage], (uint32_t)((it / kDiaTmaStages) & 1));
+    double acc[kDiaTmaR], xr[kDiaTmaR];
+    if (interior) {
+      const double *const sm = stage0 + (size_t)stage * L.stage_doubles;
+#pragma unroll
+      for (int j = 0; j < kDiaTmaR; ++j) {
+        const int i = j * kDiaTmaRows + t;
+        xr[j] = sm[L.xc + kDiaNear + i];
+        double a = 0.0;
+#pragma unroll
+        for (int k = K - 1; k >= 0; --k) {  // most negative column first
+          const int o = (int)D.off[k];
+          double lo, xv;
+          if (D.off[k] <= kDiaNear) { lo = sm[L.un[k] + i]; xv = sm[L.xc + kDiaNear + i - o]; }
+          else { lo = sm[L.ul[k] + i]; xv = sm[L.xl[k] + i + (o & 1)]; }
+          if (lo != 0.0) a = __dadd_rn(a, __dmul_rn(lo, xv));
+        }
+        a = __dadd_rn(a, UNIT ? xr[j] : __dmul_rn(sm[L.dg + i], xr[j]));
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int o = (int)D.off[k];
+          double up, xv;
+          if (D.off[k] <= kDiaNear) { up = sm[L.un[k] + i + o]; xv = sm[L.xc + kDiaNear + i + o]; }
+          else { up = sm[L.uu[k] + i + (o & 1)]; xv = sm[L.xu[k] + i + (o & 1)]; }
+          if (up != 0.0) a = __dadd_rn(a, __dmul_rn(up, xv));
+        }
+        acc[j] = a;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kDiaTmaR; ++j) {
+        const int64_t r = r0 + j * kDiaTmaRows + t;
+        xr[j] = 0.0;
+        acc[j] = 0.0;
+        if (r < nrows) {
+          xr[j] = x[r];
+          acc[j] = dia_row_direct<K, UNIT>(D, x, r, xr[j]);
+        }
+      }
+    }
+    // the stage can be refilled as soon as every lane of this warp has read it
+    __syncwarp();
+    if ((t & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
+#pragma unroll
+    for (int j = 0; j < kDiaTmaR; ++j) {
+      const int64_t r = r0 + j * kDiaTmaRows + t;
+      if (r < nrows) {
+        double a = acc[j];
+        if (!UNIT && sigma != 0.0) a += sigma * (Dvec ? Dvec[r] : 1.0) * xr[j];
+        y[r] = a;
+        dot += xr[j] * a;
+      }
+    }
+  }
+  if (DOT) {
+    // u.Au: one partial per CTA; the CTA drawing the last ticket folds them in CTA order
+    double s = warp_sum(dot);
+    if ((t & 31) == 0) wsum[t >> 5] = s;
+    dia_consumer_sync();
+    if (t == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < kDiaTmaRows / 32; ++w) tot += wsum[w];
+      partials[blockIdx.x] = tot;
+      __threadfence();
+      *is_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    }
+    dia_consumer_sync();
+    if (*is_last) {
+      __threadfence();
+      double q = 0.0;
+      for (unsigned int i = t; i < gridDim.x; i += kDiaTmaRows) q += __ldcg(&partials[i]);
+      q = warp_sum(q);
+      dia_consumer_sync();
+      if ((t & 31) == 0) wsum[t >> 5] = q;
+      dia_consumer_sync();
+      if (t == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < kDiaTmaRows / 32; ++w) tot += wsum[w];
+        const bool ok = finalize_mode != 2 || peer_allreduce_thread(pr, &tot, 1, scal);
+        scal->red[0] = tot;
+        if (ok && finalize_mode >= 1) scal->uc = tot;
+      }
+    }
+  }
+}
+
+}  // namespace fvb

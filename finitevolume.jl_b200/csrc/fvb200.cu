@@ -12,6 +12,7 @@
 #include "assemble.cuh"
 #include "common.cuh"
 #include "dia.cuh"
+#include "dia_tma.cuh"
 #include "grid.cuh"
 #include "nccl_dyn.h"
 #include "pcg.cuh"
@@ -34,6 +35,8 @@ struct PeerState {
   void *opened_u[kMaxRanks] = {};       // cudaIpcOpenMemHandle results (to close)
   void *opened_mail[kMaxRanks] = {};
   PeerTable tab = {};
+  PeerTable *d_tab = nullptr;           // device copy of tab for the in-kernel all-reduce (peer_base.cuh)
+  bool fused = true;                    // reducing kernels finish their sums across the ranks themselves
   HaloPlanDev push = {}, wait = {};
   unsigned long long red_seq = 0, halo_seq = 0;
   std::vector<uint8_t> last_blobs;      // what the open mappings correspond to
@@ -101,6 +104,9 @@ void free_problem(fvb_handle h) {
   dfree(h, h->send_rows); dfree(h, h->sendbuf);
   dfree(h, h->g_e1); dfree(h, h->g_e2); dfree(h, h->g_face); dfree(h, h->g_dh); dfree(h, h->g_src);
   for (auto &u : h->dia_U) dfree(h, u);
+  for (auto &u : h->dia_S) dfree(h, u);
+  dfree(h, h->sinv);
+  h->scale_state = 0;
   h->dia_on = false;
   h->dia_K = 0;
   if (h->mg) {
@@ -191,6 +197,19 @@ int halo_exchange(fvb_handle h, double *vec) {
   return FVB_OK;
 }
 
+// How a reducing kernel of the Jacobi-PCG closes its sums (pcg.cuh: finalize_mode): 1 single rank,
+// 2 in-kernel all-reduce over peer memory (the sequence number is drawn here), 0 separate all-reduce.
+int red_mode(fvb_handle h, PeerRed *pr) {
+  *pr = PeerRed{nullptr, 0ull};
+  if (h->nranks == 1) return 1;
+  if (h->peer && h->peer->active && h->peer->fused && h->peer->d_tab) {
+    pr->tab = h->peer->d_tab;
+    pr->seq = ++h->peer->red_seq;
+    return 2;
+  }
+  return 0;
+}
+
 // Sum scal->red[0..count) over the ranks and advance the recurrence (mode: FIN_*).
 int allreduce_fin(fvb_handle h, int count, int mode) {
   if (h->nranks == 1) return FVB_OK;
@@ -211,13 +230,56 @@ int allreduce_fin(fvb_handle h, int count, int mode) {
   return FVB_OK;
 }
 
+// The TMA-staged diagonal kernel (dia_tma.cuh) needs more than 48 KB of dynamic shared memory: opt in
+// once per instantiation and device (again only if a larger layout shows up).
+template <bool DOT, int K, bool UNIT>
+int launch_dia_tma(fvb_handle h, int n, const DiaDesc &D, const DiaTmaLayout &L, const double *vec, double *out,
+                   double sigma, int fin, PeerRed pr) {
+  static int opted[64] = {};
+  const int smem = (int)dia_tma_smem_bytes(L);
+  const int dev = h->device & 63;
+  if (opted[dev] < smem) {
+    FVB_CUDA(cudaFuncSetAttribute(k_spmv_dia_tma<DOT, K, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    opted[dev] = smem;
+  }
+  const int ntiles = cdiv(n, kDiaTmaTile);
+  const int grid = std::max(1, std::min(ntiles, h->num_sms * kDiaTmaCtasPerSm));
+  k_spmv_dia_tma<DOT, K, UNIT><<<grid, kDiaTmaThreads, smem, h->stream>>>(n, D, L, vec, out, h->Dvec, sigma, h->partials,
+                                                                        h->ticket, h->scal, fin, pr);
+  return FVB_OK;
+}
+
+// Which diagonal kernel serves this launch: the TMA pipeline when (almost) all tiles are interior
+// tiles and every slice is 16-byte aligned, else the per-thread-load kernel of dia.cuh.
+bool use_dia_tma(fvb_handle h, const double *vec, const DiaTmaLayout &L, bool scaled) {
+  if (h->fmt_request == 2) return false;
+  const int64_t n = h->nf_local, T = kDiaTmaTile;
+  auto misaligned = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
+  if ((vec && misaligned(vec)) || misaligned(h->diag)) return false;
+  for (int k = 0; k < h->dia_K; ++k)
+    if (misaligned(scaled ? h->dia_S[k] : h->dia_U[k])) return false;
+  if (dia_tma_smem_bytes(L) > 200 * 1024) return false;
+  if (h->fmt_request == 3) return true;
+  const int64_t ntiles = (n + T - 1) / T;
+  const int64_t first = (L.reach + T - 1) / T, last = (n - T - L.reach) >= 0 ? (n - T - L.reach) / T : -1;
+  const int64_t interior = std::max<int64_t>(0, last - first + 1);
+  return interior * 10 >= ntiles * 8 && ntiles >= 4 * h->num_sms;
+}
+
 // c = (A + sigma*D) vec, vec has halo room.  With dot: also u.Au into scal (CG use).
-int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot) {
+// scaled: c = A^ vec with A^ = D^-1/2 A D^-1/2 (build_scaled must have succeeded; sigma = 0).
+// fuse: let the kernel finish u.Au across the ranks itself when the peer-memory path allows (the caller
+// must then skip allreduce_fin: *fin_out reports the finalize mode used).
+int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot, bool scaled = false, bool fuse = false,
+                int *fin_out = nullptr) {
   FVB_TRY(halo_exchange(h, vec));
   const int n = (int)h->nf_local;
+  PeerRed pr = {nullptr, 0ull};
+  int fin = h->nranks == 1 ? 1 : 0;
+  if (dot && fuse && n > 0) fin = red_mode(h, &pr);
+  if (fin_out) *fin_out = fin;
   if (n == 0) return FVB_OK;
   const int grid = std::min(cdiv(n, kSpmvRows), h->num_sms * kSpmvCtasPerSm);
-  const int fin = h->nranks == 1 ? 1 : 0;
   const size_t smem = sizeof(SpmvSmem);
   int sample = -1;
   if (dot && h->prof_stride > 0 && h->prof_count < 64 && (h->prof_seen++ % h->prof_stride) == 0) {
@@ -227,29 +289,36 @@ int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot) 
   if (h->dia_on && h->fmt_request != 1) {
     DiaDesc D;
     D.K = h->dia_K;
-    for (int k = 0; k < kDiaMaxOff; ++k) { D.off[k] = h->dia_off[k]; D.U[k] = h->dia_U[k]; }
+    for (int k = 0; k < kDiaMaxOff; ++k) { D.off[k] = h->dia_off[k]; D.U[k] = scaled ? h->dia_S[k] : h->dia_U[k]; }
     D.diag = h->diag; D.row_start = h->row_start; D.nf = h->nf_local;
     D.lo0 = h->dia_lo0; D.nlo = h->dia_nlo; D.hi0 = h->dia_hi0; D.nhi = h->dia_nhi;
     const int dg = std::min(cdiv(n, kBlock * kDiaRowsPerThread), h->num_sms * kDiaCtasPerSm);
-#define FVB_DIA_LAUNCH(DOTV, KV)                                                                              \
-  k_spmv_dia<DOTV, KV><<<dg, kBlock, 0, h->stream>>>(n, D, vec, out, h->Dvec, sigma, h->partials, h->ticket, \
-                                                     h->scal, fin)
-#define FVB_DIA_K(DOTV)                                   \
-  switch (D.K) {                                          \
-    case 1: FVB_DIA_LAUNCH(DOTV, 1); break;               \
-    case 2: FVB_DIA_LAUNCH(DOTV, 2); break;               \
-    case 3: FVB_DIA_LAUNCH(DOTV, 3); break;               \
-    default: FVB_DIA_LAUNCH(DOTV, 4); break;              \
+    const DiaTmaLayout L = dia_tma_layout(D.K, D.off, scaled);
+    const bool tma = use_dia_tma(h, vec, L, scaled);
+#define FVB_DIA_LAUNCH(DOTV, KV, UV)                                                                                \
+  if (tma) FVB_TRY((launch_dia_tma<DOTV, KV, UV>(h, n, D, L, vec, out, sigma, fin, pr)));                             \
+  else k_spmv_dia<DOTV, KV, UV><<<dg, kBlock, 0, h->stream>>>(n, D, vec, out, h->Dvec, sigma, h->partials, h->ticket, \
+                                                              h->scal, fin, pr)
+#define FVB_DIA_K(DOTV, UV)                                   \
+  switch (D.K) {                                              \
+    case 1: FVB_DIA_LAUNCH(DOTV, 1, UV); break;               \
+    case 2: FVB_DIA_LAUNCH(DOTV, 2, UV); break;               \
+    case 3: FVB_DIA_LAUNCH(DOTV, 3, UV); break;               \
+    default: FVB_DIA_LAUNCH(DOTV, 4, UV); break;              \
   }
-    if (dot) { FVB_DIA_K(true) } else { FVB_DIA_K(false) }
+    if (scaled) { if (dot) { FVB_DIA_K(true, true) } else { FVB_DIA_K(false, true) } }
+    else if (dot) { FVB_DIA_K(true, false) } else { FVB_DIA_K(false, false) }
+    h->last_dia_tma = tma;
 #undef FVB_DIA_K
 #undef FVB_DIA_LAUNCH
-  } else if (dot)
+  } else if (scaled)
+    return set_error(FVB_ERR_STATE, "scaled SpMV requested without the diagonal format");
+  else if (dot)
     k_spmv<true><<<grid, kSpmvThreads, smem, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
-                                                     h->partials, h->ticket, h->scal, fin);
+                                                     h->partials, h->ticket, h->scal, fin, pr);
   else
     k_spmv<false><<<grid, kSpmvThreads, smem, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
-                                                      h->partials, h->ticket, h->scal, fin);
+                                                      h->partials, h->ticket, h->scal, fin, pr);
   if (sample >= 0) cudaEventRecord(h->prof_ev[2 * sample + 1], h->stream);
   h->tm.kernel_launches++;
   return FVB_OK;
@@ -260,8 +329,11 @@ int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot) 
 int build_dia(fvb_handle h, bool structure) {
   cudaStream_t st = h->stream;
   const int n = (int)h->nf_local;
+  h->scale_state = 0;  // the values change: the scaled copy (build_scaled) is stale
   if (structure) {
     for (auto &u : h->dia_U) dfree(h, u);
+    for (auto &u : h->dia_S) dfree(h, u);
+    dfree(h, h->sinv);
     h->dia_on = false;
     h->dia_K = 0;
     if (n < 2 || h->nnz == 0) return FVB_OK;
@@ -324,6 +396,17 @@ int build_dia(fvb_handle h, bool structure) {
     h->dia_K = K;
     h->dia_lo0 = lo0; h->dia_nlo = nlo; h->dia_hi0 = hi0; h->dia_nhi = nhi;
     h->dia_on = true;
+    // Room for the Jacobi-scaled copy (build_scaled) is taken here, in the same place of every
+    // assembly, so that repeated assemble/solve cycles reach a steady allocation pattern in the
+    // stream-ordered pool; if it does not fit, build_scaled tries again or stays unscaled.
+    if (h->scale_request != 1) {
+      bool ok = dalloc(h, &h->sinv, n) == FVB_OK;
+      for (int k = 0; k < K && ok; ++k) ok = dalloc(h, &h->dia_S[k], (int64_t)n + o[k]) == FVB_OK;
+      if (!ok) {
+        for (auto &u : h->dia_S) dfree(h, u);
+        dfree(h, h->sinv);
+      }
+    }
   }
   if (!h->dia_on) return FVB_OK;
   for (int k = 0; k < h->dia_K; ++k)
@@ -332,6 +415,63 @@ int build_dia(fvb_handle h, bool structure) {
                                              h->dia_off[0], h->dia_off[1], h->dia_off[2], h->dia_off[3], h->dia_U[0],
                                              h->dia_U[1], h->dia_U[2], h->dia_U[3]);
   h->tm.kernel_launches++;
+  return FVB_OK;
+}
+
+// Symmetric Jacobi scaling of the diagonal copy: S_k = D^-1/2 U_k D^-1/2, sinv = diag^-1/2 (dia.cuh).
+// Built lazily by the first cold-started steady Jacobi solve after the values changed.  Uses h->u as
+// scratch (its halo slots receive the neighbours' s through the ordinary halo exchange).  All ranks
+// must run the same recurrence, so the outcome is agreed over the communicator: scale_state = 1
+// only if every rank has the diagonal format and a strictly positive diagonal.
+int build_scaled(fvb_handle h) {
+  if (h->scale_state != 0) return FVB_OK;
+  cudaStream_t st = h->stream;
+  const int64_t n = h->nf_local;
+  int mine = (h->dia_on && n > 0) ? 1 : 0;
+  int *d_flag = nullptr;
+  FVB_TRY(dalloc(h, &d_flag, 1));
+  FVB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  if (mine) {
+    bool ok = true;
+    if (!h->sinv) ok = dalloc(h, &h->sinv, n) == FVB_OK;
+    for (int k = 0; k < h->dia_K && ok; ++k)
+      if (!h->dia_S[k]) ok = dalloc(h, &h->dia_S[k], n + h->dia_off[k]) == FVB_OK;
+    if (!ok) {  // not enough memory for the second copy: stay on the unscaled recurrence
+      for (auto &u : h->dia_S) dfree(h, u);
+      dfree(h, h->sinv);
+      mine = 0;
+    }
+  }
+  if (mine) {
+    k_make_sinv<<<vgrid(h, n), kBlock, 0, st>>>(n, h->diag, h->u, h->sinv, d_flag);
+    h->tm.kernel_launches++;
+  }
+  int flag = 1;
+  if (h->nranks > 1 && !(h->comm && h->comm->comm)) mine = 0;
+  else if (h->nranks > 1) {
+    // flag <- max over ranks of (bad diagonal | no diagonal format)
+    if (!mine) { flag = 1; FVB_CUDA(cudaMemcpyAsync(d_flag, &flag, sizeof(int), cudaMemcpyHostToDevice, st)); }
+    FVB_NCCL(nccl().AllReduce(d_flag, d_flag, 1, ncclInt, ncclMax, h->comm->comm, st));
+  }
+  cudaError_t e = memcpy_sync(st, &flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+  dfree(h, d_flag);
+  if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+  if (!mine || flag) { h->scale_state = 2; return FVB_OK; }
+  FVB_TRY(halo_exchange(h, h->u));
+  DiaDesc D;
+  D.K = h->dia_K;
+  for (int k = 0; k < kDiaMaxOff; ++k) { D.off[k] = h->dia_off[k]; D.U[k] = h->dia_U[k]; }
+  D.diag = h->diag; D.row_start = h->row_start; D.nf = h->nf_local;
+  D.lo0 = h->dia_lo0; D.nlo = h->dia_nlo; D.hi0 = h->dia_hi0; D.nhi = h->dia_nhi;
+  const int g = vgrid(h, n);
+  switch (D.K) {
+    case 1: k_dia_scale<1><<<g, kBlock, 0, st>>>((int)n, D, h->u, h->dia_S[0], h->dia_S[1], h->dia_S[2], h->dia_S[3]); break;
+    case 2: k_dia_scale<2><<<g, kBlock, 0, st>>>((int)n, D, h->u, h->dia_S[0], h->dia_S[1], h->dia_S[2], h->dia_S[3]); break;
+    case 3: k_dia_scale<3><<<g, kBlock, 0, st>>>((int)n, D, h->u, h->dia_S[0], h->dia_S[1], h->dia_S[2], h->dia_S[3]); break;
+    default: k_dia_scale<4><<<g, kBlock, 0, st>>>((int)n, D, h->u, h->dia_S[0], h->dia_S[1], h->dia_S[2], h->dia_S[3]); break;
+  }
+  h->tm.kernel_launches++;
+  h->scale_state = 1;
   return FVB_OK;
 }
 
@@ -529,24 +669,41 @@ int pcg_mg_run(fvb_handle h, const double *rhs, bool have_x0, double rtol, int64
                int *converged);
 
 // Jacobi-PCG on (A + sigma*D) x = rhs.  x0 (if any) already sits in h->x.  Result in h->x.
+// Cold-started steady solves on the diagonal format run the symmetrically scaled recurrence
+// (pcg.cuh, SC = true): same iterates in exact arithmetic, 112 instead of 128 bytes per row.
 int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double rtol, int64_t maxiter,
             int64_t *iters, int *converged) {
   const int64_t n = h->nf_local;
   cudaStream_t st = h->stream;
-  const int fin = h->nranks == 1 ? 1 : 0;
   const int vg = vgrid(h, n);
+  PeerRed pr;
+  int fin;
   FVB_TRY(ensure_hist(h, maxiter));
   h->prof_seen = 0;
   h->prof_count = 0;
-  k_set_scal<<<1, 1, 0, st>>>(h->scal, rtol, (long long)maxiter, (long long)h->hist_cap);
-  k_make_dinv<<<vg, kBlock, 0, st>>>(n, h->diag, h->Dvec, sigma, h->dinv);
-  h->tm.kernel_launches += 2;
-  if (have_x0) {
-    FVB_CUDA(cudaMemcpyAsync(h->u, h->x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-    FVB_TRY(launch_spmv(h, h->u, h->c, sigma, false));
+  bool sc = false;
+  if (sigma == 0.0 && !have_x0 && h->scale_request != 1 && h->fmt_request != 1) {  // rank-uniform conditions
+    FVB_TRY(build_scaled(h));
+    sc = h->scale_state == 1;
   }
-  k_pcg_init<<<vg, kBlock, 0, st>>>(n, rhs, h->c, have_x0 ? 1 : 0, h->dinv, h->x, h->r, h->partials, h->ticket,
-                                    h->scal, fin);
+  h->last_solve_scaled = sc;
+  k_set_scal<<<1, 1, 0, st>>>(h->scal, rtol, (long long)maxiter, (long long)h->hist_cap);
+  h->tm.kernel_launches++;
+  if (sc) {
+    fin = red_mode(h, &pr);
+    k_pcg_init<true><<<vg, kBlock, 0, st>>>(n, rhs, nullptr, 0, h->sinv, h->x, h->r, h->partials, h->ticket,
+                                            h->scal, fin, pr);
+  } else {
+    k_make_dinv<<<vg, kBlock, 0, st>>>(n, h->diag, h->Dvec, sigma, h->dinv);
+    h->tm.kernel_launches++;
+    if (have_x0) {
+      FVB_CUDA(cudaMemcpyAsync(h->u, h->x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+      FVB_TRY(launch_spmv(h, h->u, h->c, sigma, false));
+    }
+    fin = red_mode(h, &pr);
+    k_pcg_init<false><<<vg, kBlock, 0, st>>>(n, rhs, h->c, have_x0 ? 1 : 0, h->dinv, h->x, h->r, h->partials,
+                                             h->ticket, h->scal, fin, pr);
+  }
   h->tm.kernel_launches++;
   if (!fin) FVB_TRY(allreduce_fin(h, 2, FIN_INIT));
   // Enqueue iterations in batches; poll the device scalars one batch behind so the GPU
@@ -558,11 +715,14 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
   while (!stop) {
     int64_t todo = std::min<int64_t>(batch, maxiter - enq);
     for (int64_t it = 0; it < todo; ++it) {
-      k_update_u<<<vg, kBlock, 0, st>>>(n, h->dinv, h->r, h->u, h->x, h->scal);
+      if (sc) k_update_u<true><<<vg, kBlock, 0, st>>>(n, nullptr, h->r, h->u, h->x, h->scal);
+      else k_update_u<false><<<vg, kBlock, 0, st>>>(n, h->dinv, h->r, h->u, h->x, h->scal);
       h->tm.kernel_launches++;
-      FVB_TRY(launch_spmv(h, h->u, h->c, sigma, true));
+      FVB_TRY(launch_spmv(h, h->u, h->c, sigma, true, sc, true, &fin));
       if (!fin) FVB_TRY(allreduce_fin(h, 1, FIN_UC));
-      k_update_xr<<<vg, kBlock, 0, st>>>(n, h->c, h->dinv, h->r, h->partials, h->ticket, h->scal, h->hist, fin);
+      fin = red_mode(h, &pr);
+      if (sc) k_update_xr<true><<<vg, kBlock, 0, st>>>(n, h->c, h->diag, h->r, h->partials, h->ticket, h->scal, h->hist, fin, pr);
+      else k_update_xr<false><<<vg, kBlock, 0, st>>>(n, h->c, h->dinv, h->r, h->partials, h->ticket, h->scal, h->hist, fin, pr);
       h->tm.kernel_launches++;
       if (!fin) FVB_TRY(allreduce_fin(h, 2, FIN_ITER));
     }
@@ -578,7 +738,8 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
     if (enq >= maxiter) stop = true;
     if (batch < 64) batch *= 2;
   }
-  k_finish_x<<<vg, kBlock, 0, st>>>(n, h->u, h->x, h->scal);
+  if (sc) k_finish_x_scaled<<<vg, kBlock, 0, st>>>(n, h->u, h->sinv, h->x, h->scal);
+  else k_finish_x<<<vg, kBlock, 0, st>>>(n, h->u, h->x, h->scal);
   h->tm.kernel_launches++;
   FVB_CUDA(cudaStreamSynchronize(st));
   FVB_CUDA(memcpy_sync(h->stream, &h->scal_host[0], h->scal, sizeof(PcgScal), cudaMemcpyDeviceToHost));
@@ -610,6 +771,7 @@ int pcg_mg_run(fvb_handle h, const double *rhs, bool have_x0, double rtol, int64
   const int vg = vgrid(h, n);
   MgState &M = *h->mg;
   FVB_TRY(ensure_hist(h, maxiter));
+  h->last_solve_scaled = false;
   h->prof_seen = 0;
   h->prof_count = 0;
   k_set_scal<<<1, 1, 0, st>>>(h->scal, rtol, (long long)maxiter, (long long)h->hist_cap);
@@ -619,8 +781,8 @@ int pcg_mg_run(fvb_handle h, const double *rhs, bool have_x0, double rtol, int64
     FVB_CUDA(cudaMemcpyAsync(h->u, h->x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
     FVB_TRY(launch_spmv(h, h->u, h->c, 0.0, false));
   }
-  k_pcg_init<<<vg, kBlock, 0, st>>>(n, rhs, h->c, have_x0 ? 1 : 0, h->dinv, h->x, h->r, h->partials, h->ticket,
-                                    h->scal, fin);
+  k_pcg_init<false><<<vg, kBlock, 0, st>>>(n, rhs, h->c, have_x0 ? 1 : 0, h->dinv, h->x, h->r, h->partials, h->ticket,
+                                           h->scal, fin, PeerRed{nullptr, 0ull});
   h->tm.kernel_launches++;
   if (!fin) FVB_TRY(allreduce_fin(h, 2, FIN_INIT));
   int64_t enq = 0;
@@ -713,6 +875,11 @@ int fvb_create(int device, fvb_handle *out) {
   FVB_CUDA(cudaSetDevice(device));
   fvb_handle h = new fvb_handle_s();
   h->device = device;
+  if (const char *env = getenv("FVB_PCG_SCALING")) h->scale_request = atoi(env) == 0 ? 1 : 0;  // A/B measurements
+  if (const char *env = getenv("FVB_SPMV_FORMAT")) {  // initial fvb_set_spmv_format value
+    const int f = atoi(env);
+    if (f >= 0 && f <= 3) h->fmt_request = f;
+  }
   FVB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto &ev : h->ev) FVB_CUDA(cudaEventCreate(&ev));
   FVB_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -746,6 +913,7 @@ int fvb_destroy(fvb_handle h) {
       if (h->peer->opened_mail[r]) cudaIpcCloseMemHandle(h->peer->opened_mail[r]);
     }
     if (h->peer->mail) cudaFree(h->peer->mail);
+    if (h->peer->d_tab) cudaFree(h->peer->d_tab);
     delete h->peer;
   }
   if (h->nranks > 1 && h->u) cudaFree(h->u);
@@ -1316,6 +1484,9 @@ int fvb_peer_import(fvb_handle h, const uint8_t *blobs, const int64_t *send_dst_
   }
   // send_rows is laid out peer after peer in plan order; push.send_begin indexes it directly
   // only if peers without sends contribute nothing, which holds because their count is 0.
+  if (!P.d_tab) FVB_CUDA(cudaMalloc((void **)&P.d_tab, sizeof(PeerTable)));
+  FVB_CUDA(memcpy_sync(h->stream, P.d_tab, &P.tab, sizeof(PeerTable), cudaMemcpyHostToDevice));
+  if (const char *env = getenv("FVB_FUSED_ALLREDUCE")) P.fused = atoi(env) != 0;
   P.active = true;
   return FVB_OK;
 }
@@ -1507,17 +1678,36 @@ int fvb_time_spmv(fvb_handle h, int warmup, int reps, double *ms_avg) {
 
 int fvb_set_spmv_format(fvb_handle h, int fmt) {
   FVB_TRY(check_handle(h, false));
-  if (fmt != 0 && fmt != 1) return set_error(FVB_ERR_BAD_INPUT, "format must be 0 (auto) or 1 (CSR)");
+  if (fmt < 0 || fmt > 3)
+    return set_error(FVB_ERR_BAD_INPUT, "format must be 0 (auto), 1 (CSR), 2 (diagonal, per-thread loads) or 3 (diagonal, TMA)");
   h->fmt_request = fmt;
-  if (fmt == 0 && h->assembled && !h->dia_on) FVB_TRY(build_dia(h, true));
+  if (fmt != 1 && h->assembled && !h->dia_on) FVB_TRY(build_dia(h, true));
   return FVB_OK;
 }
 
 int fvb_get_spmv_format(fvb_handle h, int *active, int *n_offsets) {
   FVB_TRY(check_handle(h, true));
   const bool dia = h->dia_on && h->fmt_request != 1;
-  if (active) *active = dia ? 2 : 1;
+  int kind = 1;
+  if (dia) {
+    const DiaTmaLayout L = dia_tma_layout(h->dia_K, h->dia_off, false);
+    kind = use_dia_tma(h, h->u, L, false) ? 3 : 2;  // (h->u may not exist yet: alignment is then taken for granted)
+  }
+  if (active) *active = kind;
   if (n_offsets) *n_offsets = dia ? h->dia_K : 0;
+  return FVB_OK;
+}
+
+int fvb_set_pcg_scaling(fvb_handle h, int mode) {
+  FVB_TRY(check_handle(h, false));
+  if (mode != 0 && mode != 1) return set_error(FVB_ERR_BAD_INPUT, "scaling mode must be 0 (auto) or 1 (off)");
+  h->scale_request = mode;
+  return FVB_OK;
+}
+
+int fvb_get_pcg_scaling(fvb_handle h, int *last_solve_scaled) {
+  FVB_TRY(check_handle(h, true));
+  if (last_solve_scaled) *last_solve_scaled = h->last_solve_scaled ? 1 : 0;
   return FVB_OK;
 }
 

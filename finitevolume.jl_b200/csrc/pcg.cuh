@@ -5,13 +5,26 @@
 //     c = Pl \ r ; rho_prev = rho ; rho = c.r ; beta = rho/rho_prev ; u = c + beta u
 //     c = A u ; alpha = rho / u.c ; x += alpha u ; r -= alpha c ; residual = ||r||
 //     stop when residual <= tol * ||r0|| or iteration == maxiter
+// finalize_mode of the reducing kernels: 0 = leave the local sums in scal->red (an NCCL all-reduce and a
+// k_fin_* launch follow), 1 = single rank: advance the recurrence in the last CTA, 2 = sum over the ranks
+// through NVLink peer memory in the last CTA (peer_base.cuh), then advance the recurrence.
 // One iteration = three launches: k_update_u, k_spmv<DOT>, k_update_xr.  The update x += alpha u
 // of iteration k is deferred into k_update_u of iteration k+1, where u is read anyway (saves one
 // pass over u per iteration); k_finish_x applies the last one after the loop.  All scalars stay
 // in device memory (PcgScal); every kernel returns at once when scal->done is set, so the
 // host can enqueue iterations in batches without synchronising.
+//
+// SC = true: the same recurrence on the symmetrically scaled system A^ x^ = b^ with
+// A^ = D^-1/2 A D^-1/2 (unit diagonal), x^ = D^1/2 x, b^ = D^-1/2 b.  In exact arithmetic Jacobi-PCG
+// on A and plain CG on A^ produce the same iterates (u^ = D^1/2 u, r^ = D^-1/2 r, rho = r^.r^ =
+// r.D^-1 r, u^.A^u^ = u.Au), but the vector kernels no longer read D^-1 and the SpMV no longer reads
+// diag(A): 40 + 40 + 32 = 112 bytes per row and iteration instead of 48 + 48 + 32 = 128.  The
+// stopping rule stays the reference's: ||r||_2 = sqrt(sum d_i r^_i^2) is accumulated from diag(A)
+// in k_update_xr and written to the history.  x is unscaled by k_finish_x.  Used for cold-started
+// steady solves on the diagonal format (fvb200.cu: pcg_run).
 #pragma once
 #include "common.cuh"
+#include "peer_base.cuh"
 #include "reduce.cuh"
 
 namespace fvb {
@@ -58,29 +71,41 @@ __global__ void k_make_dinv(int64_t n, const double *__restrict__ diag, const do
 }
 
 // r = rhs - c (c = A x0, when have_x0) or r = rhs, x = 0; sums (dinv r).r and r.r
+// SC (cold start only): dinv carries s = diag^-1/2; r^ = s .* rhs, x^ = 0; sums r^.r^ and rhs.rhs
+template <bool SC>
 __global__ void __launch_bounds__(kBlock)
 k_pcg_init(int64_t n, const double *__restrict__ rhs, const double *__restrict__ c, int have_x0,
            const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r,
-           double *partials, unsigned int *ticket, PcgScal *scal, int finalize_mode) {
+           double *partials, unsigned int *ticket, PcgScal *scal, int finalize_mode, PeerRed pr) {
   double s0 = 0.0, s1 = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     double ri;
-    if (have_x0) ri = rhs[i] - c[i];
+    if (!SC && have_x0) ri = rhs[i] - c[i];
     else { ri = rhs[i]; x[i] = 0.0; }
-    r[i] = ri;
-    s0 += dinv[i] * ri * ri;
+    if (SC) {
+      const double rs = dinv[i] * ri;
+      r[i] = rs;
+      s0 += rs * rs;
+    } else {
+      r[i] = ri;
+      s0 += dinv[i] * ri * ri;
+    }
     s1 += ri * ri;
   }
   s0 = block_sum(s0);
   s1 = block_sum(s1);
   double t0, t1;
   if (last_block_sum2(s0, s1, partials, ticket, &t0, &t1)) {
-    scal->red[0] = t0; scal->red[1] = t1;
-    if (finalize_mode == 1) pcg_finish_init(scal, t0, t1);
+    double v[2] = {t0, t1};
+    const bool ok = finalize_mode != 2 || peer_allreduce_thread(pr, v, 2, scal);  // 2: sum over the ranks here
+    scal->red[0] = v[0]; scal->red[1] = v[1];
+    if (ok && finalize_mode >= 1) pcg_finish_init(scal, v[0], v[1]);
   }
 }
 
 // x += alpha_prev * u (the deferred update of the previous iteration); u = dinv .* r + beta * u
+// SC: u^ = r^ + beta * u^ (dinv is not read)
+template <bool SC>
 __global__ void __launch_bounds__(kBlock)
 k_update_u(int64_t n, const double *__restrict__ dinv, const double *__restrict__ r, double *__restrict__ u,
            double *__restrict__ x, const PcgScal *__restrict__ scal) {
@@ -90,35 +115,44 @@ k_update_u(int64_t n, const double *__restrict__ dinv, const double *__restrict_
   const double ap = scal->alpha_prev;
   if (first) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-      u[i] = dinv[i] * r[i];
+      u[i] = SC ? r[i] : dinv[i] * r[i];
   } else {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
       const double ui = u[i];
       x[i] += ap * ui;
-      u[i] = dinv[i] * r[i] + beta * ui;
+      u[i] = (SC ? r[i] : dinv[i] * r[i]) + beta * ui;
     }
   }
 }
 
 // r -= alpha c ; sums (dinv r).r and r.r ; last block closes the iteration
+// SC: dinv carries diag(A): sums r^.r^ (= r.D^-1 r) and diag .* r^ . r^ (= r.r, the reference's residual)
+template <bool SC>
 __global__ void __launch_bounds__(kBlock)
 k_update_xr(int64_t n, const double *__restrict__ c, const double *__restrict__ dinv, double *__restrict__ r,
-            double *partials, unsigned int *ticket, PcgScal *scal, double *hist, int finalize_mode) {
+            double *partials, unsigned int *ticket, PcgScal *scal, double *hist, int finalize_mode, PeerRed pr) {
   if (scal->done) return;
   const double alpha = scal->rho / scal->uc;
   double s0 = 0.0, s1 = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double ri = r[i] - alpha * c[i];
     r[i] = ri;
-    s0 += dinv[i] * ri * ri;
-    s1 += ri * ri;
+    if (SC) {
+      s0 += ri * ri;
+      s1 += dinv[i] * ri * ri;
+    } else {
+      s0 += dinv[i] * ri * ri;
+      s1 += ri * ri;
+    }
   }
   s0 = block_sum(s0);
   s1 = block_sum(s1);
   double t0, t1;
   if (last_block_sum2(s0, s1, partials, ticket, &t0, &t1)) {
-    scal->red[0] = t0; scal->red[1] = t1;
-    if (finalize_mode == 1) pcg_finish_iter(scal, t0, t1, hist);
+    double v[2] = {t0, t1};
+    const bool ok = finalize_mode != 2 || peer_allreduce_thread(pr, v, 2, scal);
+    scal->red[0] = v[0]; scal->red[1] = v[1];
+    if (ok && finalize_mode >= 1) pcg_finish_iter(scal, v[0], v[1], hist);
   }
 }
 
@@ -129,6 +163,14 @@ k_finish_x(int64_t n, const double *__restrict__ u, double *__restrict__ x, PcgS
   if (ap == 0.0) return;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     x[i] += ap * u[i];
+}
+// scaled variant: x = s .* (x^ + alpha_prev u^)
+__global__ void __launch_bounds__(kBlock)
+k_finish_x_scaled(int64_t n, const double *__restrict__ u, const double *__restrict__ sinv, double *__restrict__ x,
+                  PcgScal *scal) {
+  const double ap = scal->alpha_prev;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = sinv[i] * (ap == 0.0 ? x[i] : x[i] + ap * u[i]);
 }
 
 // ---- small vector helpers for the transient path (src/transient.jl:71, :81) ---------------

@@ -15,52 +15,16 @@
 // reductions later, which cannot start before every rank consumed the previous use (the next
 // reduction needs every rank's contribution, made after that rank finished reading).
 // Every spin is bounded (kPeerTimeoutNs); on timeout the solve is flagged and stops.
+// The reducing kernels of the Jacobi-PCG perform the same all-reduce themselves in their last CTA
+// (peer_base.cuh: peer_allreduce_thread, finalize_mode 2); k_allreduce_fin remains for the multigrid
+// PCG, the global norms of the transient stepper and FVB_FUSED_ALLREDUCE=0.
 #pragma once
 #include "common.cuh"
 #include "mg.cuh"
 #include "pcg.cuh"
+#include "peer_base.cuh"
 
 namespace fvb {
-
-constexpr int kMaxRanks = 8;
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
-
-struct PeerMail {
-  double vals[2][kMaxRanks][4];            // [parity][source rank][value]
-  unsigned long long vseq[2][kMaxRanks];   // sequence number of the values above
-  unsigned long long hseq[kMaxRanks];      // last halo push received from each source rank
-  int error;                               // set locally when a wait timed out
-};
-
-struct PeerTable {
-  PeerMail *mail[kMaxRanks];  // mail[r] = rank r's mailbox as mapped into THIS process (mail[rank] local)
-  double *u[kMaxRanks];       // u[r]    = rank r's search-direction vector (owned rows + halo slots)
-  int nranks, rank;
-};
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// spin until *flag >= want; false on timeout
-__device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long want) {
-  if (ld_acquire_sys(flag) >= want) return true;
-  const unsigned long long t0 = globaltimer_ns();
-  while (ld_acquire_sys(flag) < want) {
-    if (globaltimer_ns() - t0 > kPeerTimeoutNs) return false;
-    __nanosleep(64);
-  }
-  return true;
-}
 
 // ---- halo ------------------------------------------------------------------------------------------------
 struct HaloPlanDev {

@@ -17,6 +17,7 @@
 // 4 CTAs per SM, so the "last CTA folds the partials" ticket costs ~600 atomics, not 5e5).
 #pragma once
 #include "common.cuh"
+#include "peer_base.cuh"
 #include "reduce.cuh"
 #include "tma.cuh"
 
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm)
 k_spmv(int nrows, const int *__restrict__ rowptr, const int *__restrict__ colidx,
        const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
        const double *__restrict__ Dvec, double sigma, double *__restrict__ partials,
-       unsigned int *ticket, PcgScal *scal, int finalize_mode) {
+       unsigned int *ticket, PcgScal *scal, int finalize_mode, PeerRed pr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SpmvSmem &S = *reinterpret_cast<SpmvSmem *>(smem_raw);
   if (DOT && scal->done) return;
@@ -144,8 +145,9 @@ k_spmv(int nrows, const int *__restrict__ rowptr, const int *__restrict__ colidx
       if (t == 0) {
         double tot = 0.0;
         for (int w = 0; w < kSpmvRows / 32; ++w) tot += S.wsum[w];
+        const bool ok = finalize_mode != 2 || peer_allreduce_thread(pr, &tot, 1, scal);
         scal->red[0] = tot;
-        if (finalize_mode == 1) scal->uc = tot;
+        if (ok && finalize_mode >= 1) scal->uc = tot;
       }
     }
   }

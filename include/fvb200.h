@@ -192,9 +192,28 @@ int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes);
  * diagonals (regulargrid numbering, src/grid.jl:60); if so the solver streams an index-free
  * symmetric-diagonal copy (8*(K+1)+16 bytes per row) instead of the CSR arrays
  * (12*nnz_row+20).  The CSR arrays stay resident either way (fvb_get_csr).
- *   fmt: 0 = automatic (default), 1 = always CSR.   active: 1 = CSR, 2 = diagonal. */
+ * Two kernels serve the diagonal copy: a persistent TMA pipeline (cp.async.bulk slices of every
+ * operand into shared memory, dia_tma.cuh) when almost all row tiles are interior to the owned
+ * range, else a per-thread-load kernel (dia.cuh).  All three kernels give bit-identical products.
+ *   fmt: 0 = automatic (default), 1 = always CSR, 2 = diagonal with per-thread loads only,
+ *        3 = diagonal through the TMA pipeline whatever the size (2, 3: CSR if the pattern does
+ *        not qualify).  The environment variable FVB_SPMV_FORMAT presets it at fvb_create.
+ *   active: 1 = CSR, 2 = diagonal (per-thread loads), 3 = diagonal (TMA pipeline). */
 int fvb_set_spmv_format(fvb_handle h, int fmt);
 int fvb_get_spmv_format(fvb_handle h, int *active, int *n_offsets);
+
+/* ---- symmetric Jacobi scaling of the steady solve ------------------------------------------
+ * Jacobi-PCG on A x = b (src/FiniteVolume.jl:160-161 with Pl = diag(A)) generates, in exact
+ * arithmetic, the same iterates as plain CG on A^ x^ = b^ with A^ = D^-1/2 A D^-1/2 (unit
+ * diagonal), x^ = D^1/2 x, b^ = D^-1/2 b.  When the diagonal format is active the library keeps
+ * such a scaled copy and runs cold-started steady solves (fvb_solve without x0) on it: no D^-1
+ * and no diag(A) reads inside the iteration (112 instead of 128 bytes per row).  The residual
+ * norm tested and recorded is still the reference's ||b - A x||_2.  Heads agree with the unscaled
+ * recurrence to solver tolerance; iteration counts can differ by rounding (+-1).
+ *   mode: 0 = automatic (default), 1 = never (always the unscaled recurrence).
+ * fvb_get_pcg_scaling reports whether the LAST fvb_solve on this handle ran scaled. */
+int fvb_set_pcg_scaling(fvb_handle h, int mode);
+int fvb_get_pcg_scaling(fvb_handle h, int *last_solve_scaled);
 
 /* ---- device-side grid helpers (src/grid.jl:56-110, :14-33) ---------------------------------
  * Same ordering and bit-identical values as the reference's serial loops, produced directly in

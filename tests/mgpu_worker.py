@@ -38,6 +38,7 @@ def main():
     s.assemble(nb, aol, kf, src_all[lo - 1:hi], dn, dh, None, True, n_nodes=N, node_range=(lo, hi))
     fvd.exchange_halo_plan(s)
     head, x, ch = s.solve(rtol=1e-12, want_x=True)
+    scaled = s.pcg_scaling()  # slab-partitioned boxes keep the diagonal format => scaled recurrence on every rank
     # multigrid: every rank preconditions with the V-cycle of its own diagonal block
     s.set_preconditioner("mg")
     head_mg, _, ch_mg = s.solve(rtol=1e-12)
@@ -54,9 +55,13 @@ def main():
     it_t, conv_t = s.step(0, 1, 25.0, 2, rtol=1e-12)
     dnorm = s.vec_diffnorm(1, 2)
     step_loc = s.vec_download(2)
+    # the unscaled recurrence on the same distributed system
+    s.set_pcg_scaling(1)
+    head_un, _, ch_un = s.solve(rtol=1e-12)
+    s.set_pcg_scaling(0)
     out = [None] * world
     dist.all_gather_object(out, (head, y_loc, ch.iters, ch.isconverged, step_loc, dnorm, conv_t, head_mg, ch_mg.iters,
-                                 ch_mg.isconverged, mg_kind))
+                                 ch_mg.isconverged, mg_kind, scaled, head_un, ch_un.iters))
     ok = True
     if rank == 0:
         from oracle import fv_oracle as orc
@@ -82,11 +87,15 @@ def main():
         mg_ok = (err_mg <= 1e-8 and all(o[9] for o in out) and len({o[8] for o in out}) == 1
                  and all(o[10] == "mg" for o in out) and out[0][8] * 3 < out[0][2])
         iters = {o[2] for o in out}
-        ok = (err_h <= 1e-8 and err_y <= 1e-12 and err_s <= 1e-8 and len(iters) == 1 and all(o[3] for o in out)
+        hun = np.concatenate([o[12] for o in out])
+        sc_ok = (len({o[11] for o in out}) == 1 and np.max(np.abs(hun - ho)) <= 1e-8 * np.max(np.abs(ho))
+                 and len({o[13] for o in out}) == 1 and abs(out[0][13] - out[0][2]) <= 2)
+        ok = (sc_ok and err_h <= 1e-8 and err_y <= 1e-12 and err_s <= 1e-8 and len(iters) == 1 and all(o[3] for o in out)
               and abs(out[0][5] - dn_ref) <= 1e-10 * dn_ref and all(o[6] for o in out)
               and abs(out[0][2] - cho.iters) <= 3 and mg_ok)
         print(f"MGPU world={world} ns={ns} err_head={err_h:.2e} err_spmv={err_y:.2e} err_step={err_s:.2e} "
-              f"iters={sorted(iters)} oracle_iters={cho.iters} mg_iters={out[0][8]} err_mg={err_mg:.2e} ok={ok}", flush=True)
+              f"iters={sorted(iters)} oracle_iters={cho.iters} mg_iters={out[0][8]} err_mg={err_mg:.2e} "
+              f"scaled={out[0][11]} iters_unscaled={out[0][13]} ok={ok}", flush=True)
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
     dist.barrier()

@@ -381,6 +381,112 @@ def test_theis_transient(fv, orc):
     assert np.max(np.abs(us[-1] - uso[-1])) <= 1e-6
 
 
+def test_scaled_recurrence_matches_unscaled(fv, orc):
+    """Cold-started steady Jacobi solves on the diagonal format run CG on D^-1/2 A D^-1/2 (unit diagonal, no
+    D^-1 reads).  Same iterates as Jacobi-PCG on A up to rounding: heads, iteration count and the recorded
+    ||b - A x|| history must agree with the unscaled recurrence and with the oracle; warm starts, forced CSR
+    and the transient operator keep the unscaled recurrence."""
+    nb, aol, lnkf, src, dn, dh, vol = box_problem(fv, [19, 12, 9], 1.5)
+    src = 1e-6 * np.random.default_rng(5).standard_normal(src.size)
+    src[dn - 1] = 0
+    s = fv.System().assemble(nb, aol, lnkf, src, dn, dh, None, True)
+    assert s.spmv_format() == ("dia", 3)
+    head_sc, x_sc, ch_sc = s.solve(rtol=RT_TIGHT, want_x=True)
+    assert s.pcg_scaling() and ch_sc.isconverged
+    s.set_pcg_scaling(1)
+    head_un, x_un, ch_un = s.solve(rtol=RT_TIGHT, want_x=True)
+    assert not s.pcg_scaling() and ch_un.isconverged
+    assert abs(ch_sc.iters - ch_un.iters) <= 2
+    assert np.allclose(head_sc, head_un, rtol=1e-9, atol=1e-12)
+    m = min(ch_sc.iters, ch_un.iters, 60)
+    assert np.allclose(ch_sc.data["resnorm"][:m], ch_un.data["resnorm"][:m], rtol=1e-6)
+    # the recorded norm is the true residual ||b - A x|| of the UNSCALED system (checked where rounding
+    # in b - A x is far below the residual itself)
+    b = s.b()
+    assert len(ch_sc.data["resnorm"]) == ch_sc.iters
+    _, x8, c8 = s.solve(rtol=1e-8, want_x=True)
+    rtrue = np.linalg.norm(b - s.spmv(x8))
+    assert c8.isconverged and abs(c8.data["resnorm"][-1] - rtrue) <= 1e-3 * rtrue and rtrue <= 1e-8 * np.linalg.norm(b)
+    ho, cho, *_ = orc.solvediffusion(nb, aol, lnkf, src, dn, dh, maxiter=20000, tol=RT_TIGHT, logtransformconductivity=True)
+    assert np.max(np.abs(head_sc - ho)) <= 1e-8 * np.max(np.abs(ho)) and abs(ch_sc.iters - cho.iters) <= 3
+    # default tolerance, maxiter cap, zero iterations
+    s.set_pcg_scaling(0)
+    h1, _, c1 = s.solve()
+    assert s.pcg_scaling() and c1.isconverged and c1.data["resnorm"][-1] <= fv.SQRT_EPS * np.linalg.norm(b)
+    h5, _, c5 = s.solve(maxiter=5)
+    assert not c5.isconverged and c5.iters == 5 and len(c5.data["resnorm"]) == 5
+    assert np.allclose(c5.data["resnorm"], ch_un.data["resnorm"][:5], rtol=1e-8)
+    h0, x0_, c0 = s.solve(maxiter=0, want_x=True)
+    assert c0.iters == 0 and not np.any(x0_)
+    # warm start / CSR / transient step: unscaled recurrence
+    # (the stopping rule is relative to the INITIAL residual, as in IterativeSolvers.cg: a warm start from a
+    # converged x0 iterates again)
+    hw, _, cw = s.solve(rtol=1e-3, x0=x_sc)
+    assert not s.pcg_scaling() and cw.isconverged and np.allclose(hw, head_sc, rtol=1e-9, atol=1e-12)
+    s.set_spmv_format(1)
+    s.solve()
+    assert not s.pcg_scaling()
+    s.set_spmv_format(0)
+    # values-only update must refresh the scaled copy
+    lnk2 = lnkf + 0.3 * np.random.default_rng(6).standard_normal(lnkf.size)
+    s.update_values(lnk2)
+    hu, _, cu = s.solve(rtol=RT_TIGHT)
+    assert s.pcg_scaling()
+    hf, _, cf = fv.System().assemble(nb, aol, lnk2, src, dn, dh, None, True).solve(rtol=RT_TIGHT)
+    assert np.array_equal(hu, hf) and cu.iters == cf.iters
+    # repeated solves are bitwise reproducible
+    hu2, _, cu2 = s.solve(rtol=RT_TIGHT)
+    assert np.array_equal(hu, hu2) and cu2.iters == cu.iters
+    # a thin sheet: offsets 1, 2, 34
+    nb2, aol2, k2, src2, dn2, dh2, _ = box_problem(fv, [30, 17, 2], 1.0)
+    s2 = fv.System().assemble(nb2, aol2, k2, src2, dn2, dh2, None, True)
+    if s2.spmv_format()[0] == "dia":
+        g, _, cg2 = s2.solve(rtol=RT_TIGHT)
+        go, *_ = orc.solvediffusion(nb2, aol2, k2, src2, dn2, dh2, maxiter=20000, tol=RT_TIGHT, logtransformconductivity=True)
+        assert s2.pcg_scaling() and np.max(np.abs(g - go)) <= 1e-8
+
+
+@pytest.mark.parametrize("ns", [[40, 64, 64], [100, 100, 2], [60, 150, 2], [50, 33, 7], [60, 5, 9], [18, 11, 7],
+                                [700, 2, 2]])
+def test_dia_tma_kernel_bitwise(fv, ns):
+    """The TMA-staged diagonal kernel (dia_tma.cuh) against the per-thread-load kernel and the CSR kernel:
+    bit-identical products (interior tiles from shared memory, edge tiles from global memory; near and far,
+    even and odd offsets), the same solves, the transient operator."""
+    nb, aol, lnkf, src, dn, dh, vol = box_problem(fv, ns, 1.2)
+    src = 1e-6 * np.random.default_rng(4).standard_normal(src.size)
+    src[dn - 1] = 0
+    s = fv.System().assemble(nb, aol, lnkf, src, dn, dh, None, True)
+    if s.spmv_format()[0] != "dia":
+        pytest.skip("pattern not diagonal")
+    x = np.random.default_rng(8).standard_normal(s.sizes()["nf_local"])
+    s.set_spmv_format(3)
+    assert s.spmv_kernel() == "dia_tma"
+    y_tma = s.spmv(x)
+    h_tma, _, c_tma = s.solve(rtol=RT_TIGHT)
+    assert s.pcg_scaling()
+    s.set_pcg_scaling(1)
+    h_tma_un, _, c_tma_un = s.solve(rtol=RT_TIGHT)
+    s.set_pcg_scaling(0)
+    s.set_spmv_format(2)
+    assert s.spmv_kernel() == "dia"
+    y_ld = s.spmv(x)
+    h_ld, _, c_ld = s.solve(rtol=RT_TIGHT)
+    s.set_spmv_format(1)
+    y_csr = s.spmv(x)
+    assert np.array_equal(y_tma, y_ld) and np.array_equal(y_tma, y_csr)
+    assert c_tma.isconverged and c_tma_un.isconverged and abs(c_tma.iters - c_ld.iters) <= 2
+    assert np.allclose(h_tma, h_ld, rtol=1e-9, atol=1e-12) and np.allclose(h_tma_un, h_ld, rtol=1e-9, atol=1e-12)
+    # transient operator A + D/dt
+    s.set_storage(0.1, vol)
+    outs = []
+    for fmt in (3, 2):
+        s.set_spmv_format(fmt)
+        s.vec_load_b(0); s.vec_upload(1, x)
+        it, conv = s.step(0, 1, 13.0, 2, rtol=1e-12)
+        outs.append((it, s.vec_download(2)))
+    assert abs(outs[0][0] - outs[1][0]) <= 1 and np.allclose(outs[0][1], outs[1][1], rtol=1e-9, atol=1e-12)
+
+
 def test_diagonal_format_matches_csr(fv, orc, fourfractures):
     """The index-free symmetric-diagonal copy is picked for regulargrid numbering and must give the
     same products and the same solve as the CSR kernel; irregular graphs stay on CSR."""
