@@ -6,14 +6,18 @@
 //     x[r0 +- o_k .. +T)   neighbour values       x[r0 .. +T), diag[r0 .. +T)
 // so one elected producer lane can ask the TMA unit (cp.async.bulk -> UBLKCP) for all of them and
 // the eight consumer warps only ever touch shared memory: no LSU/L1 wavefronts, no address
-// arithmetic and no registers are spent on the streams, and two tiles per CTA (four per SM) are
-// in flight regardless of occupancy.  The plane-distance re-reads (lower diagonals, x[r +- n2*n3])
-// are served by L2 exactly as in k_spmv_dia: the grid is resident (2 CTAs/SM) and tiles are dealt
-// round-robin, so the sweep is a moving front thinner than one plane.
+// arithmetic and no registers are spent on the streams, and two or three tiles per SM are in flight
+// regardless of occupancy.  The plane-distance re-reads (lower diagonals, x[r +- n2*n3]) are served
+// by L2 exactly as in k_spmv_dia: the grid is resident (1 CTA/SM) and tiles are dealt round-robin,
+// so the sweep is a moving front thinner than one plane.
 //
-// Offsets o_k <= kDiaNear (the z-neighbour, o = 1) are served from the centre slices, which are
-// fetched with a margin; larger offsets get their own slices, started one element early when o_k is
-// odd so that every copy stays 16-byte aligned.
+// What bounds this product on B200 is not HBM but the L2 slices (ncu: ~11.7 TB/s of L2->SM traffic,
+// the LTS throughput cap, at 6 TB/s of DRAM traffic): every re-read of a neighbour's value or of a
+// lower diagonal is an L2 transaction.  Hence the tile is long (T = 1024 rows) and every offset
+// o_k <= T/2 is "near": its neighbours x[r +- o_k] and its lower entries come out of the tile's own
+// centre slices, fetched once with a margin of o_k (z- AND y-neighbours on grids up to 512 points
+// per axis: 76 instead of 88 bytes of L2 traffic per row).  Larger offsets get their own slices,
+// started one element early when o_k is odd so that every copy stays 16-byte aligned.
 //
 // Tiles whose slices would leave the owned range [0, nf) -- the first and last plane of a slab,
 // where columns live in the halo or do not exist -- are "edge" tiles: the producer completes the
@@ -28,40 +32,52 @@
 
 namespace fvb {
 
-constexpr int kDiaTmaRows = 256;                        // consumer threads per CTA
+constexpr int kDiaTmaRows = 512;                        // consumer threads per CTA
 constexpr int kDiaTmaR = 2;                             // rows per consumer thread and tile
 constexpr int kDiaTmaTile = kDiaTmaRows * kDiaTmaR;     // T
 constexpr int kDiaTmaThreads = kDiaTmaRows + 32;        // + producer warp
-constexpr int kDiaTmaStages = 2;
-constexpr int kDiaTmaCtasPerSm = 2;
-constexpr int kDiaNear = 8;                             // margin of the centre slices (even)
+constexpr int kDiaTmaMaxStages = 3;
+constexpr int kDiaTmaCtasPerSm = 1;
+constexpr int kDiaNearMax = kDiaTmaTile / 2;            // offsets up to here are served by the centre slices
+constexpr int kDiaTmaSmemMax = 227 * 1024;              // dynamic shared memory one CTA may opt in to
 
 // Per-stage layout in doubles (filled on the host: dia_tma_layout).
 struct DiaTmaLayout {
-  int xc;            // x[r0 - kDiaNear .. r0 + T + kDiaNear)
+  int margin;        // M = largest near offset rounded up to even (>= 2)
+  int xc;            // x[r0 - M .. r0 + T + M)
   int dg;            // diag[r0 .. r0 + T)                                  (unused when UNIT)
-  int un[kDiaMaxOff];  // near k: U_k[r0 .. r0 + T + kDiaNear)
+  int un[kDiaMaxOff];  // near k: U_k[r0 .. r0 + T + even(o_k))
   int xl[kDiaMaxOff];  // far k:  x[(r0 - o_k) & ~1 .. + T + 2)
   int xu[kDiaMaxOff];  // far k:  x[(r0 + o_k) & ~1 .. + T + 2)
   int ul[kDiaMaxOff];  // far k:  U_k[r0 .. r0 + T)
   int uu[kDiaMaxOff];  // far k:  U_k[(o_k + r0) & ~1 .. + T + 2)
   int stage_doubles; // size of one stage
+  int stages;        // 3 if they fit into shared memory, else 2 (0: does not fit at all)
   int bar_off;       // byte offset of the mbarriers / reduction scratch behind the stages
   uint32_t tx_bytes; // bytes one interior tile brings in
   int64_t reach;     // interior tiles satisfy r0 >= reach and r0 + T + reach <= nf
 };
 
+inline int dia_even_up(int64_t o) { return (int)((o + 1) & ~(int64_t)1); }
+inline size_t dia_tma_tail_bytes() {
+  return 2 * kDiaTmaMaxStages * sizeof(uint64_t) + (kDiaTmaRows / 32) * sizeof(double) + 16;
+}
+
 inline DiaTmaLayout dia_tma_layout(int K, const int64_t *off, bool unit) {
   DiaTmaLayout L = {};
   const int T = kDiaTmaTile;
-  int p = 0, n = 0;
-  auto take = [&](int len) { int at = p; p += len; n += len; return at; };
-  L.xc = take(T + 2 * kDiaNear);
+  int M = 2;
+  for (int k = 0; k < K; ++k)
+    if (off[k] <= kDiaNearMax) M = std::max(M, dia_even_up(off[k]));
+  L.margin = M;
+  int p = 0;
+  auto take = [&](int len) { int at = p; p += len; return at; };
+  L.xc = take(T + 2 * M);
   if (!unit) L.dg = take(T);
-  int64_t reach = kDiaNear;
+  int64_t reach = M;
   for (int k = 0; k < K; ++k) {
-    if (off[k] <= kDiaNear) {
-      L.un[k] = take(T + kDiaNear);
+    if (off[k] <= kDiaNearMax) {
+      L.un[k] = take(T + dia_even_up(off[k]));
     } else {
       L.xl[k] = take(T + 2);
       L.xu[k] = take(T + 2);
@@ -71,14 +87,15 @@ inline DiaTmaLayout dia_tma_layout(int K, const int64_t *off, bool unit) {
     }
   }
   L.stage_doubles = p;
-  L.tx_bytes = (uint32_t)n * 8u;
-  L.bar_off = kDiaTmaStages * p * 8;
+  L.tx_bytes = (uint32_t)p * 8u;
+  L.stages = 0;
+  for (int st = kDiaTmaMaxStages; st >= 2 && !L.stages; --st)
+    if ((size_t)st * p * 8 + dia_tma_tail_bytes() <= (size_t)kDiaTmaSmemMax) L.stages = st;
+  L.bar_off = std::max(L.stages, 1) * p * 8;
   L.reach = reach;
   return L;
 }
-inline size_t dia_tma_smem_bytes(const DiaTmaLayout &L) {
-  return (size_t)L.bar_off + 2 * kDiaTmaStages * sizeof(uint64_t) + (kDiaTmaRows / 32) * sizeof(double) + 16;
-}
+inline size_t dia_tma_smem_bytes(const DiaTmaLayout &L) { return (size_t)L.bar_off + dia_tma_tail_bytes(); }
 
 __device__ __forceinline__ void dia_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kDiaTmaRows) : "memory"); }
 
@@ -118,13 +135,14 @@ k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ 
   constexpr int T = kDiaTmaTile;
   double *const stage0 = reinterpret_cast<double *>(smem_raw);
   uint64_t *const full = reinterpret_cast<uint64_t *>(smem_raw + L.bar_off);
-  uint64_t *const empty = full + kDiaTmaStages;
-  double *const wsum = reinterpret_cast<double *>(empty + kDiaTmaStages);
+  uint64_t *const empty = full + kDiaTmaMaxStages;
+  double *const wsum = reinterpret_cast<double *>(empty + kDiaTmaMaxStages);
+  const int nstages = L.stages, M = L.margin;
   int *const is_last = reinterpret_cast<int *>(wsum + kDiaTmaRows / 32);
   const int t = threadIdx.x;
   const int ntiles = (nrows + T - 1) / T;
   if (t == 0) {
-    for (int s = 0; s < kDiaTmaStages; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kDiaTmaRows / 32);
     }
@@ -135,31 +153,32 @@ k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ 
   if (t >= kDiaTmaRows) {
     // ---------------- producer warp: one elected lane drives the TMA unit ----------------
     if (t == kDiaTmaRows) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int stage = it % kDiaTmaStages;
-        if (it >= kDiaTmaStages) mbar_wait(&empty[stage], (uint32_t)((it / kDiaTmaStages - 1) & 1));
+      int stage = 0, use = 0;  // use = how often this stage has been filled before
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (use > 0) mbar_wait(&empty[stage], (uint32_t)((use - 1) & 1));
+        const int cur = stage;
+        if (++stage == nstages) { stage = 0; ++use; }
         const int64_t r0 = (int64_t)tile * T;
         const bool interior = r0 >= L.reach && r0 + T + L.reach <= (int64_t)nrows;
         if (!interior) {
-          mbar_expect_tx(&full[stage], 0u);  // nothing to copy: the consumers read global memory
+          mbar_expect_tx(&full[cur], 0u);  // nothing to copy: the consumers read global memory
           continue;
         }
-        double *const sm = stage0 + (size_t)stage * L.stage_doubles;
-        mbar_expect_tx(&full[stage], L.tx_bytes);
-        bulk_g2s(sm + L.xc, x + (r0 - kDiaNear), (T + 2 * kDiaNear) * 8u, &full[stage]);
-        if (!UNIT) bulk_g2s(sm + L.dg, D.diag + r0, T * 8u, &full[stage]);
+        double *const sm = stage0 + (size_t)cur * L.stage_doubles;
+        mbar_expect_tx(&full[cur], L.tx_bytes);
+        bulk_g2s(sm + L.xc, x + (r0 - M), (uint32_t)(T + 2 * M) * 8u, &full[cur]);
+        if (!UNIT) bulk_g2s(sm + L.dg, D.diag + r0, T * 8u, &full[cur]);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           const int64_t o = D.off[k];
-          if (o <= kDiaNear) {
-            bulk_g2s(sm + L.un[k], D.U[k] + r0, (T + kDiaNear) * 8u, &full[stage]);
+          if (o <= kDiaNearMax) {
+            bulk_g2s(sm + L.un[k], D.U[k] + r0, (uint32_t)(T + (int)((o + 1) & ~(int64_t)1)) * 8u, &full[cur]);
           } else {
             const int64_t sh = o & 1;
-            bulk_g2s(sm + L.xl[k], x + (r0 - o - sh), (T + 2) * 8u, &full[stage]);
-            bulk_g2s(sm + L.xu[k], x + (r0 + o - sh), (T + 2) * 8u, &full[stage]);
-            bulk_g2s(sm + L.ul[k], D.U[k] + r0, T * 8u, &full[stage]);
-            bulk_g2s(sm + L.uu[k], D.U[k] + (r0 + o - sh), (T + 2) * 8u, &full[stage]);
+            bulk_g2s(sm + L.xl[k], x + (r0 - o - sh), (T + 2) * 8u, &full[cur]);
+            bulk_g2s(sm + L.xu[k], x + (r0 + o - sh), (T + 2) * 8u, &full[cur]);
+            bulk_g2s(sm + L.ul[k], D.U[k] + r0, T * 8u, &full[cur]);
+            bulk_g2s(sm + L.uu[k], D.U[k] + (r0 + o - sh), (T + 2) * 8u, &full[cur]);
           }
         }
       }
@@ -167,27 +186,29 @@ k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ 
     return;
   }
 
-  // ---------------- consumers: thread t owns rows r0 + t, r0 + 256 + t of every tile ----------------
+  // ---------------- consumers: thread t owns rows r0 + t, r0 + kDiaTmaRows + t of every tile ----------------
   double dot = 0.0;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int stage = it % kDiaTmaStages;
+  int nxt = 0, use = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int stage = nxt;
+    const uint32_t parity = (uint32_t)(use & 1);
+    if (++nxt == nstages) { nxt = 0; ++use; }
     const int64_t r0 = (int64_t)tile * T;
     const bool interior = r0 >= L.reach && r0 + T + L.reach <= (int64_t)nrows;
-    mbar_wait(&full[stage], (uint32_t)((it / kDiaTmaStages) & 1));
+    mbar_wait(&full[stage], parity);
     double acc[kDiaTmaR], xr[kDiaTmaR];
     if (interior) {
       const double *const sm = stage0 + (size_t)stage * L.stage_doubles;
 #pragma unroll
       for (int j = 0; j < kDiaTmaR; ++j) {
         const int i = j * kDiaTmaRows + t;
-        xr[j] = sm[L.xc + kDiaNear + i];
+        xr[j] = sm[L.xc + M + i];
         double a = 0.0;
 #pragma unroll
         for (int k = K - 1; k >= 0; --k) {  // most negative column first
           const int o = (int)D.off[k];
           double lo, xv;
-          if (D.off[k] <= kDiaNear) { lo = sm[L.un[k] + i]; xv = sm[L.xc + kDiaNear + i - o]; }
+          if (D.off[k] <= kDiaNearMax) { lo = sm[L.un[k] + i]; xv = sm[L.xc + M + i - o]; }
           else { lo = sm[L.ul[k] + i]; xv = sm[L.xl[k] + i + (o & 1)]; }
           if (lo != 0.0) a = __dadd_rn(a, __dmul_rn(lo, xv));
         }
@@ -196,7 +217,7 @@ k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ 
         for (int k = 0; k < K; ++k) {
           const int o = (int)D.off[k];
           double up, xv;
-          if (D.off[k] <= kDiaNear) { up = sm[L.un[k] + i + o]; xv = sm[L.xc + kDiaNear + i + o]; }
+          if (D.off[k] <= kDiaNearMax) { up = sm[L.un[k] + i + o]; xv = sm[L.xc + M + i + o]; }
           else { up = sm[L.uu[k] + i + (o & 1)]; xv = sm[L.xu[k] + i + (o & 1)]; }
           if (up != 0.0) a = __dadd_rn(a, __dmul_rn(up, xv));
         }

@@ -258,7 +258,7 @@ bool use_dia_tma(fvb_handle h, const double *vec, const DiaTmaLayout &L, bool sc
   if ((vec && misaligned(vec)) || misaligned(h->diag)) return false;
   for (int k = 0; k < h->dia_K; ++k)
     if (misaligned(scaled ? h->dia_S[k] : h->dia_U[k])) return false;
-  if (dia_tma_smem_bytes(L) > 200 * 1024) return false;
+  if (L.stages == 0) return false;  // one stage pair does not fit into shared memory
   if (h->fmt_request == 3) return true;
   const int64_t ntiles = (n + T - 1) / T;
   const int64_t first = (L.reach + T - 1) / T, last = (n - T - L.reach) >= 0 ? (n - T - L.reach) / T : -1;
