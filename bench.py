@@ -11,14 +11,17 @@ default tolerance (rtol = sqrt(eps), IterativeSolvers default) and the scatter t
   e2e        the same step through the public call with pinned HOST inputs: host->device copies of
              neighbors/areasoverlengths/conductivities/sources/Dirichlet lists and the device->host
              read of the heads are inside the timed region (host clock bracketed by synchronisation)
-  roofline   the CSR SpMV kernel (dominant): algorithmic bytes 12*nnz + 4*(Nf+1) + 16*Nf per launch
-             over its mean launch time, sampled in situ with CUDA events inside the timed solves
+  roofline   the SpMV kernel of the timed solves (dominant), sampled in situ with CUDA events: on this
+             workload the symmetric-diagonal TMA kernel on the Jacobi-scaled copy, 8*K + 16 = 40
+             algorithmic bytes per row; `csr_kernel` gives the general CSR kernel timed alone against
+             12*nnz + 4*(Nf+1) + 16*Nf
   cpu_baseline / --impl reference
              the CPU restatement of the reference path (oracle/, all host threads) on a bounded
              sample, extrapolated to the workload (the Julia reference itself cannot run here)
 
 N > 1: launched by torchrun, one rank per GPU; the grid is slab-partitioned by x-plane (strong
-scaling: the global problem is fixed), halo planes and CG scalars travel over NCCL.
+scaling: the global problem is fixed), halo planes and CG scalars travel over NVLink peer memory
+(the CG all-reduces inside the reducing kernels) or, with FVB_P2P=0, over NCCL.
 """
 from __future__ import annotations
 
@@ -359,6 +362,7 @@ def main():
     wall = time.perf_counter() - w0
     launches = sysm.timings()["kernel_launches"] - l0
     scaled = sysm.pcg_scaling()  # the timed solves ran the symmetrically scaled recurrence (unit-diagonal SpMV)
+    kern = sysm.spmv_kernel()    # "csr" | "dia" (per-thread loads) | "dia_tma" (TMA pipeline)
     clocks = sampler.stop()
     last_tm = sysm.timings()
     sz = sysm.sizes()
@@ -487,13 +491,15 @@ def main():
             "e2e_device_grid": devgrid,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm",
-                         "kernel": ("k_spmv_dia<true,%d,%s> (symmetric-diagonal SpMV%s + fused u.Au)"
-                                    % (fmt_k, "true" if scaled else "false",
+                         "kernel": ("%s<true,%d,%s> (symmetric-diagonal SpMV%s + fused u.Au)"
+                                    % ("k_spmv_dia_tma" if kern == "dia_tma" else "k_spmv_dia", fmt_k,
+                                       "true" if scaled else "false",
                                        " on the Jacobi-scaled unit-diagonal copy" if scaled else "")) if fmt == "dia"
                          else "k_spmv<true> (CSR SpMV + fused u.Au)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                          "avg_launch_ms": spmv_avg_ms, "launches_sampled": int(spmv_samples), "format": fmt,
+                         "spmv_kernel": kern,
                          "csr_equivalent_gbs": (csr_bytes / (spmv_avg_ms * 1e-3) / 1e9) if spmv_samples else None,
                          "csr_kernel": csr_roof,
                          "note": "rank-local rows; min over ranks" if world > 1 else "sampled inside the timed solves"},

@@ -42,6 +42,7 @@ struct PcgScal {
   int done, converged;
 };
 
+class Arena;      // arena.h
 struct Comm;      // nccl_dyn.h
 struct PeerState; // fvb200.cu (peer.cuh tables)
 struct MgState;   // fvb200.cu (mg.cuh hierarchy)
@@ -53,6 +54,7 @@ struct fvb_handle_s {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
   int num_sms = 148;
+  fvb::Arena *arena = nullptr;  // device-memory arena (arena.h); null: cudaMallocAsync pool (FVB_ARENA=0)
 
   // ---- partition -------------------------------------------------------------------
   int64_t n_nodes = 0;          // global N

@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cstdlib>
 
+#include "arena.h"
 #include "assemble.cuh"
 #include "common.cuh"
 #include "dia.cuh"
@@ -62,13 +63,31 @@ using namespace fvb;
 
 namespace {
 
-// Stream-ordered allocation from the device's memory pool (release threshold = keep everything):
-// repeated assemblies of the same size -- inverse loops, the bench -- reuse the blocks instead of
-// paying synchronous cudaMalloc/cudaFree (a quarter of a second per step at 512^3).
+// Device memory of a handle comes from its arena (arena.h: best-fit blocks inside a few big cudaMalloc
+// chunks, so a repeated assemble -> solve sequence reuses the very same blocks without any driver call).
+// FVB_ARENA=0 selects the stream-ordered pool instead (cudaMallocAsync, release threshold = keep
+// everything), whose defragmentation stalls of up to a second per step are the reason the arena exists.
+void *arena_chunk_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void arena_chunk_free(void *p) { cudaFree(p); }
+
 template <typename T>
 int dalloc(fvb_handle h, T **p, int64_t n) {
   *p = nullptr;
   size_t bytes = sizeof(T) * (size_t)std::max<int64_t>(n, 1);
+  if (h->arena) {
+    *p = static_cast<T *>(h->arena->alloc(bytes));
+    if (!*p)
+      return set_error(FVB_ERR_OOM, "out of device memory: " + std::to_string(bytes) + " bytes requested, arena holds " +
+                                        std::to_string(h->arena->reserved()) + " (" + std::to_string(h->arena->in_use()) + " in use)");
+    return FVB_OK;
+  }
   cudaError_t e = cudaMallocAsync((void **)p, bytes, h->stream);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -78,7 +97,10 @@ int dalloc(fvb_handle h, T **p, int64_t n) {
 }
 template <typename T>
 void dfree(fvb_handle h, T *&p) {
-  if (p) cudaFreeAsync(p, h->stream);
+  if (p) {
+    if (h->arena) h->arena->free(p);
+    else cudaFreeAsync(p, h->stream);
+  }
   p = nullptr;
 }
 
@@ -875,6 +897,10 @@ int fvb_create(int device, fvb_handle *out) {
   FVB_CUDA(cudaSetDevice(device));
   fvb_handle h = new fvb_handle_s();
   h->device = device;
+  {
+    const char *env = getenv("FVB_ARENA");
+    if (!env || atoi(env) != 0) h->arena = new Arena(arena_chunk_alloc, arena_chunk_free);
+  }
   if (const char *env = getenv("FVB_PCG_SCALING")) h->scale_request = atoi(env) == 0 ? 1 : 0;  // A/B measurements
   if (const char *env = getenv("FVB_SPMV_FORMAT")) {  // initial fvb_set_spmv_format value
     const int f = atoi(env);
@@ -922,6 +948,8 @@ int fvb_destroy(fvb_handle h) {
     delete h->comm;
   }
   dfree(h, h->scal); dfree(h, h->ticket);
+  delete h->arena;  // gives every chunk back (cudaFree synchronises the device)
+  h->arena = nullptr;
   if (h->scal_host) cudaFreeHost(h->scal_host);
   for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
   for (auto &ev : h->prof_ev) if (ev) cudaEventDestroy(ev);
@@ -1723,7 +1751,8 @@ int fvb_device_alloc(fvb_handle h, int64_t bytes, void **dev_ptr) {
 
 int fvb_device_free(fvb_handle h, void *dev_ptr) {
   FVB_TRY(check_handle(h, false));
-  if (dev_ptr) FVB_CUDA(cudaFreeAsync(dev_ptr, h->stream));
+  unsigned char *p = static_cast<unsigned char *>(dev_ptr);
+  dfree(h, p);
   return FVB_OK;
 }
 

@@ -23,6 +23,22 @@ def test_library_exports_every_declared_symbol(fv):
     assert L.fvb_version() >= 100
 
 
+def test_device_arena_bookkeeping(tmp_path):
+    """csrc/arena.h (host-only bookkeeping of the handle's device memory) under ASan/UBSan with malloc-backed
+    chunks: steady state after one pass of a repeated request sequence (same addresses, no growth), no
+    overlaps, exact accounting, full coalescing, the out-of-memory / trim path."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path / "test_arena")
+    src = os.path.join(ROOT, "tests", "cpp", "test_arena.cpp")
+    subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-o", exe, src], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "arena ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_no_cpu_fallback(fv):
     import torch
     if torch.cuda.is_available():
