@@ -39,6 +39,42 @@ def test_device_arena_bookkeeping(tmp_path):
     assert r.returncode == 0 and "arena ok" in r.stdout, r.stdout + r.stderr
 
 
+def _build_c_demo(tmp_path, fv):
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.dirname(fv.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", exe, fv.LIB_PATH, f"-Wl,-rpath,{libdir}", "-lm"],
+                   check=True)
+    return exe
+
+
+def test_header_is_plain_c_and_fails_loudly_without_gpu(fv, tmp_path):
+    """include/fvb200.h compiles as pedantic C99 and the library links into a C program (the boundary has no
+    C++ or torch types); without a CUDA device that program stops at fvb_create with the no-fallback error."""
+    import subprocess
+    import torch
+    exe = _build_c_demo(tmp_path, fv)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present (see test_c_abi_demo_on_gpu)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_c_abi_demo_on_gpu(fv, tmp_path):
+    """examples/c_abi_demo.c: the reference's 4-node smoke test (test/runtests.jl:4-16) and a homogeneous box
+    with its exact linear solution, driven from plain C through the C ABI only."""
+    import subprocess
+    exe = _build_c_demo(tmp_path, fv)
+    r = subprocess.run([exe, "24"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "c_abi_demo ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_no_cpu_fallback(fv):
     import torch
     if torch.cuda.is_available():
