@@ -39,6 +39,91 @@ def test_device_arena_bookkeeping(tmp_path):
     assert r.returncode == 0 and "arena ok" in r.stdout, r.stdout + r.stderr
 
 
+def _dia_tma_model_check(L, offs, unit, nf):
+    """Replay, in numpy, what the producer lane of k_spmv_dia_tma copies for every interior tile and what the
+    consumer threads read back (csrc/dia_tma.cuh), on the layout the library's own dia_tma_layout() produced.
+    Every cp.async.bulk must be 16-byte aligned on both sides, stay inside its array, and the stage must be
+    filled exactly once; every consumer read must return the element the row sum needs."""
+    T, M, near = L["T"], L["margin"], L["near_max"]
+    X = np.arange(nf, dtype=np.int64) * 16 + 1
+    DG = np.arange(nf, dtype=np.int64) * 16 + 2
+    U = [np.arange(nf + o, dtype=np.int64) * 16 + 3 + k for k, o in enumerate(offs)]
+    even_up = lambda o: (o + 1) & ~1
+    n_interior = 0
+    for tile in range((nf + T - 1) // T):
+        r0 = tile * T
+        if not (r0 >= L["reach"] and r0 + T + L["reach"] <= nf):
+            continue
+        n_interior += 1
+        sm = np.full(L["stage_doubles"], -1, dtype=np.int64)
+        copied = 0
+
+        def cp(dst, arr, start, n):
+            nonlocal copied
+            assert start % 2 == 0 and n % 2 == 0 and dst % 2 == 0      # 16-byte alignment, size multiple of 16
+            assert 0 <= start and start + n <= arr.size and dst + n <= sm.size
+            assert np.all(sm[dst:dst + n] == -1)                       # no two copies overlap in the stage
+            sm[dst:dst + n] = arr[start:start + n]
+            copied += n
+        cp(L["xc"], X, r0 - M, T + 2 * M)
+        if not unit:
+            cp(L["dg"], DG, r0, T)
+        for k, o in enumerate(offs):
+            if o <= near:
+                cp(L["un"][k], U[k], r0, T + even_up(o))
+            else:
+                sh = o & 1
+                cp(L["xl"][k], X, r0 - o - sh, T + 2)
+                cp(L["xu"][k], X, r0 + o - sh, T + 2)
+                cp(L["ul"][k], U[k], r0, T)
+                cp(L["uu"][k], U[k], r0 + o - sh, T + 2)
+        assert copied * 8 == L["tx_bytes"] and np.all(sm != -1)
+        i = np.arange(T)
+        r = r0 + i
+        assert np.array_equal(sm[L["xc"] + M + i], X[r])
+        if not unit:
+            assert np.array_equal(sm[L["dg"] + i], DG[r])
+        for k, o in enumerate(offs):
+            if o <= near:
+                lo, xlo = sm[L["un"][k] + i], sm[L["xc"] + M + i - o]
+                up, xup = sm[L["un"][k] + i + o], sm[L["xc"] + M + i + o]
+            else:
+                sh = o & 1
+                lo, xlo = sm[L["ul"][k] + i], sm[L["xl"][k] + i + sh]
+                up, xup = sm[L["uu"][k] + i + sh], sm[L["xu"][k] + i + sh]
+            assert np.array_equal(lo, U[k][r]) and np.array_equal(xlo, X[r - o])         # A[r, r-o] * x[r-o]
+            assert np.array_equal(up, U[k][o + r]) and np.array_equal(xup, X[r + o])     # A[r, r+o] * x[r+o]
+    return n_interior
+
+
+def test_dia_tma_layout_addressing(tmp_path):
+    """Shared-memory layout of the TMA diagonal SpMV (host function dia_tma_layout in csrc/dia_tma.cuh, dumped by
+    a host-only nvcc harness) against a numpy replay of the kernel's copies and reads: near/far, odd/even
+    offsets, 1 to 4 diagonals, with and without the stored main diagonal."""
+    import json
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "dump_layout")
+    subprocess.run([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "dump_dia_tma_layout.cu")], check=True)
+    cases = [[1, 512, 262144], [1, 256, 65536], [1, 2, 200], [1, 7, 231], [1, 9, 45], [1], [1, 64, 4096],
+             [1, 1024, 1048576], [3, 513, 9999], [1, 2, 4], [511, 512, 513, 700]]
+    for offs in cases:
+        for unit in (0, 1):
+            out = subprocess.run([exe, str(unit)] + [str(o) for o in offs], capture_output=True, text=True, check=True).stdout
+            L = json.loads(out)
+            assert L["stages"] >= 2 and L["smem_bytes"] <= L["smem_max"] and L["bar_off"] == L["stages"] * L["stage_doubles"] * 8
+            assert L["tx_bytes"] == L["stage_doubles"] * 8 and L["bar_off"] % 16 == 0
+            nf = min(max(offs) * 3 + 5 * L["T"] + 77, max(offs) * 2 + 40 * L["T"] + 77)
+            assert _dia_tma_model_check(L, offs, bool(unit), nf) >= 1
+    # the 512^3 steady solve: three stages of the unit-diagonal copy must fit (what the bench runs)
+    L = json.loads(subprocess.run([exe, "1", "1", "512", "262144"], capture_output=True, text=True, check=True).stdout)
+    assert L["stages"] == 3 and L["margin"] == 512
+
+
 def _build_c_demo(tmp_path, fv):
     import shutil
     import subprocess
