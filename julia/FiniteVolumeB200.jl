@@ -106,6 +106,24 @@ function solve!(s::System; maxiter=100_000, rtol=sqrt(eps(Float64)), x0=nothing)
 	return head, ConvergenceHistory(conv[] != 0, iters[], Dict{Symbol, Any}(:resnorm=>hist[1:iters[]]))
 end
 
+# ---- solver controls (no counterpart in the reference: kernel / format / recurrence choice) -----------------
+# fmt: 0 automatic, 1 always CSR, 2 diagonal copy with per-thread loads, 3 diagonal copy through the TMA pipeline
+setspmvformat!(s::System, fmt::Integer) = (check(ccall((:fvb_set_spmv_format, libfvb), Cint, (Ptr{Cvoid}, Cint), s.h, fmt)); s)
+# mode: 0 automatic (cold-started steady solves on the diagonal copy run CG on D^-1/2 A D^-1/2), 1 never
+setpcgscaling!(s::System, mode::Integer) = (check(ccall((:fvb_set_pcg_scaling, libfvb), Cint, (Ptr{Cvoid}, Cint), s.h, mode)); s)
+# kind: 0 Jacobi (default), 1 aggregation-multigrid V-cycle (box-structured matrices); zeros = default parameters
+function setpreconditioner!(s::System, kind::Integer; nu::Integer=0, omega::Real=0.0, oc::Real=0.0)
+	check(ccall((:fvb_set_preconditioner, libfvb), Cint, (Ptr{Cvoid}, Cint, Cint, Float64, Float64), s.h, kind, nu, omega, oc))
+	return s
+end
+# values-only re-assembly on the retained structure (inverse loops, examples/box_model/ex.jl:53-64)
+function updatevalues!(s::System, conductivities::Vector, logtransformconductivity::Bool=false)
+	k = convert(Vector{Float64}, conductivities)
+	check(ccall((:fvb_update_values, libfvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ptr{Float64}),
+		s.h, k, length(k), logtransformconductivity, C_NULL, C_NULL))
+	return s
+end
+
 # ---- the reference's names ---------------------------------------------------------------------------
 # src/FiniteVolume.jl:75
 function assembleA(neighbors::Array{Pair{Int, Int}, 1}, areasoverlengths::Vector, conductivities::Vector, sources::Vector, dirichletnodes::Array{Int, 1}, dirichletheads::Vector, metaindex=nothing, logtransformconductivity::Bool=false)
