@@ -7,7 +7,7 @@ built library and a CUDA device.
 The directory name contains a dot, so load it with `__graft_entry__.load_package()` (which
 registers it as module `fvb200`) rather than a plain import statement.
 """
-from . import _lib
+from . import _lib, jld
 from ._lib import FVBError, LIB_PATH
 from .api import (ConvergenceHistory, DEFAULT_MAXITER, DeviceArray, SQRT_EPS, SparseMatrixCSC, System, assembleA, assembleb,
                   freenodes2nodes, getfreenodes, solvediffusion)
@@ -21,5 +21,5 @@ __all__ = [
     "assembleA", "assembleb", "freenodes2nodes", "getfreenodes", "solvediffusion", "grid_sizes",
     "nodehycos2neighborhycos", "regulargrid", "adaptivebackwardeulerstep", "adjointintegrate",
     "backwardeulerintegrate", "backwardeulerintegrate_generic", "fixedbackwardeulerstep", "getadjointfunctions",
-    "getcontinuoussolution", "gradientintegrate", "integrate_g", "integratedfdplambda",
+    "getcontinuoussolution", "gradientintegrate", "integrate_g", "integratedfdplambda", "jld",
 ]

@@ -296,3 +296,33 @@ def test_halo_plan_pure(fv):
     assert p2[0] == [1] and p2[1] == [1] and list(p2[2]) == [0] and p2[3] == [1]
     with pytest.raises(ValueError):
         dist.halo_plan_from_ranges(0, ranges, [np.array([5]), halos[1], halos[2]])
+
+
+REF_FRACTURES = "/root/reference/examples/fractures/fourfractures"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_FRACTURES, "mesh.jld")),
+                    reason="the reference checkout is only present in the build container")
+def test_jld_reader_against_fixture(fv, fourfractures):
+    """fv.jld.load == JLD.load of examples/fractures/ex.jl:9: every variable of the reference's mesh.jld (root
+    group in dense link storage: fractal heap) and of pflotran_solution.jld (symbol-table group) must equal the
+    committed fixture, which tests/golden/make_fixtures.py extracted independently by absolute file offsets."""
+    path = os.path.join(REF_FRACTURES, "mesh.jld")
+    want = ["xs", "ys", "zs", "neighbors", "areasoverlengths", "fractureindices", "dirichletnodes", "dirichletheads",
+            "conductivities"]
+    assert fv.jld.names(path) == sorted(want)
+    got = fv.jld.load(path, *want)  # same call shape as the reference's JLD.load(path, names...)
+    for name, arr in zip(want, got):
+        assert arr.dtype == fourfractures[name].dtype and np.array_equal(arr, fourfractures[name]), name
+    assert got[3].shape == (6314, 2) and got[3].flags["C_CONTIGUOUS"]  # ready for the C ABI's 2F interleaved int64
+    h = fv.jld.load(os.path.join(REF_FRACTURES, "pflotran_solution.jld"), "h")
+    assert np.array_equal(h, fourfractures["pflotran_h"])
+    with pytest.raises(KeyError):
+        fv.jld.load(path, "nope")
+
+
+def test_jld_reader_rejects_foreign_files(fv, tmp_path):
+    p = tmp_path / "x.jld"
+    p.write_bytes(b"not an hdf5 file" * 100)
+    with pytest.raises(fv.jld.JLDFormatError):
+        fv.jld.load(str(p))
