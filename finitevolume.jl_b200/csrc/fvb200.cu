@@ -971,6 +971,11 @@ int fvb_comm_unique_id(uint8_t id[FVB_UNIQUE_ID_BYTES]) {
 int fvb_comm_init(fvb_handle h, int nranks, int rank, const uint8_t id[FVB_UNIQUE_ID_BYTES]) {
   FVB_TRY(check_handle(h, false));
   if (nranks < 1 || rank < 0 || rank >= nranks) return set_error(FVB_ERR_BAD_INPUT, "bad rank/nranks");
+  // A problem assembled under the previous rank count owns buffers whose allocation route depends on it
+  // (u: arena when single-rank, plain cudaMalloc for IPC export otherwise): drop it while that is still known.
+  FVB_CUDA(cudaStreamSynchronize(h->stream));
+  free_problem(h);
+  if (h->nranks > 1 && h->u) { cudaFree(h->u); h->u = nullptr; h->u_cap = 0; }
   h->nranks = nranks;
   h->rank = rank;
   if (nranks == 1) return FVB_OK;

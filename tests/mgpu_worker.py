@@ -72,7 +72,10 @@ def main():
         hg = np.concatenate([o[0] for o in out])
         yg = np.concatenate([o[1] for o in out])
         err_h = np.max(np.abs(hg - ho)) / np.max(np.abs(ho))
-        err_y = np.max(np.abs(yg - orc.spmv(Ao, xg)) / (np.abs(orc.spmv(Ao, xg)) + 1e-300))
+        # componentwise backward error of the distributed product: |y - A x| <= c * eps * (|A| |x|)  (rows of A
+        # nearly annihilate smooth vectors, so an error relative to |y| itself would only measure that cancellation)
+        Aabs = abs(Ao.toscipy().tocsr())
+        err_y = np.max(np.abs(yg - orc.spmv(Ao, xg)) / (Aabs @ np.abs(xg) + 1e-300))
         import scipy.sparse as sp
         import scipy.sparse.linalg as spla
         D = 0.1 * volg[fn]
@@ -90,7 +93,7 @@ def main():
         hun = np.concatenate([o[12] for o in out])
         sc_ok = (len({o[11] for o in out}) == 1 and np.max(np.abs(hun - ho)) <= 1e-8 * np.max(np.abs(ho))
                  and len({o[13] for o in out}) == 1 and abs(out[0][13] - out[0][2]) <= 2)
-        ok = (sc_ok and err_h <= 1e-8 and err_y <= 1e-12 and err_s <= 1e-8 and len(iters) == 1 and all(o[3] for o in out)
+        ok = (sc_ok and err_h <= 1e-8 and err_y <= 1e-14 and err_s <= 1e-8 and len(iters) == 1 and all(o[3] for o in out)
               and abs(out[0][5] - dn_ref) <= 1e-10 * dn_ref and all(o[6] for o in out)
               and abs(out[0][2] - cho.iters) <= 3 and mg_ok)
         print(f"MGPU world={world} ns={ns} err_head={err_h:.2e} err_spmv={err_y:.2e} err_step={err_s:.2e} "
