@@ -326,3 +326,17 @@ def test_jld_reader_rejects_foreign_files(fv, tmp_path):
     p.write_bytes(b"not an hdf5 file" * 100)
     with pytest.raises(fv.jld.JLDFormatError):
         fv.jld.load(str(p))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_FRACTURES, "mesh.jld")),
+                    reason="the reference checkout is only present in the build container")
+def test_fractures_example_inputs(fv, fourfractures):
+    """examples/fractures.py (= examples/fractures/ex.jl:6-17): the host side up to the solve."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fractures_example", os.path.join(ROOT, "examples", "fractures.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    p = m.load_problem(fv, REF_FRACTURES)
+    assert np.array_equal(p["neighbors"], fourfractures["neighbors"]) and not p["sources"].any()
+    f2f = m.fracture_of_face(p)
+    assert f2f.shape == (6314,) and set(np.unique(f2f)) <= {1, 2, 3, 4}
