@@ -189,3 +189,67 @@ def test_regulargrid_counts(orc):
     assert list(map(tuple, nb[:3])) == [(1, 7), (1, 3), (1, 2)]
     assert np.isclose(vol.sum(), 3 * 2 * 1)
     assert coords.shape == (3, 24) and list(coords[:, 1]) == [0.0, 0.0, 1.0]
+
+
+def _scaled_cg_numpy(S, b, tol, maxiter):
+    """Plain CG on A^ = D^-1/2 A D^-1/2, x^ = D^1/2 x, b^ = D^-1/2 b, stopping on the TRUE residual norm
+    sqrt(sum d_i r^_i^2) -- the recurrence libfvb200 runs for cold-started steady solves (csrc/pcg.cuh, SC = true),
+    restated in numpy with the same order of operations (rho = r^.r^, u^ = r^ + beta u^, c^ = A^ u^,
+    alpha = rho / u^.c^, x^ += alpha u^, r^ -= alpha c^)."""
+    import scipy.sparse as sp
+    d = S.diagonal()
+    s = 1.0 / np.sqrt(d)
+    Ah = (sp.diags(s) @ S @ sp.diags(s)).tocsr()
+    Ah.setdiag(1.0)
+    r = s * b
+    x = np.zeros_like(b)
+    u = np.zeros_like(b)
+    rho, rho_prev = float(r @ r), 1.0
+    resid0 = float(np.sqrt(b @ b))
+    hist = []
+    for it in range(maxiter):
+        beta = 0.0 if it == 0 else rho / rho_prev
+        u = r + beta * u
+        c = Ah @ u
+        alpha = rho / float(u @ c)
+        x += alpha * u
+        r -= alpha * c
+        rho_prev, rho = rho, float(r @ r)
+        res = float(np.sqrt(np.sum(d * r * r)))
+        hist.append(res)
+        if res <= tol * resid0:
+            break
+    return s * x, np.array(hist)
+
+
+@pytest.mark.parametrize("case", ["box_sigma1", "box_sigma3", "fourfractures"])
+def test_scaled_recurrence_is_the_same_iteration(orc, fourfractures, case):
+    """The claim behind fvb_set_pcg_scaling (include/fvb200.h): Jacobi-PCG on A and CG on D^-1/2 A D^-1/2 are the
+    same iteration.  Checked on the CPU against the oracle's IterativeSolvers-style Jacobi-PCG: equal iteration
+    counts (+-1), equal residual histories, equal heads -- on mild and strong heterogeneity and on the irregular
+    fracture graph, at the default and at a tight tolerance."""
+    if case == "fourfractures":
+        m = fourfractures
+        nb, aol, k, dn, dh = m["neighbors"], m["areasoverlengths"], m["conductivities"], m["dirichletnodes"], m["dirichletheads"]
+        src, logk = np.zeros(m["xs"].size), False
+    else:
+        ns = [14, 12, 10]
+        _, nb, aol, _ = orc.regulargrid([0, 0, 0], [n - 1 for n in ns], ns, want_coords=False)
+        N = int(np.prod(ns))
+        sigma = 1.0 if case == "box_sigma1" else 3.0
+        lnk = np.log(1e-5) + sigma * np.random.default_rng(0).standard_normal(N)
+        k = orc.nodehycos2neighborhycos(nb, lnk, True)
+        plane = ns[1] * ns[2]
+        dn = np.concatenate([np.arange(1, plane + 1), np.arange(N - plane + 1, N + 1)])
+        dh = np.concatenate([np.ones(plane), np.zeros(plane)])
+        src, logk = np.zeros(N), True
+    A = orc.assembleA(nb, aol, k, src, dn, dh, None, logk)
+    b = orc.assembleb(nb, aol, k, src, dn, dh, None, logk)
+    S = A.toscipy().tocsr()
+    for tol in (np.sqrt(np.finfo(float).eps), 1e-12):
+        xo, cho = orc.cg(A, b, tol=tol, maxiter=100000)
+        xs, hist = _scaled_cg_numpy(S, b, tol, 100000)
+        assert cho.isconverged and abs(len(hist) - cho.iters) <= 1
+        n = min(len(hist), cho.iters) - 1
+        assert np.allclose(hist[:n], cho.data["resnorm"][:n], rtol=1e-6)
+        assert np.max(np.abs(xs - xo)) <= 1e-8 * np.max(np.abs(xo))
