@@ -340,3 +340,18 @@ def test_fractures_example_inputs(fv, fourfractures):
     assert np.array_equal(p["neighbors"], fourfractures["neighbors"]) and not p["sources"].any()
     f2f = m.fracture_of_face(p)
     assert f2f.shape == (6314,) and set(np.unique(f2f)) <= {1, 2, 3, 4}
+
+
+def test_halo_run_compression_roundtrip(fv):
+    """distributed.runs_of / cols_of: what the ranks actually exchange for their halo lists."""
+    import importlib
+    d = importlib.import_module("fvb200.distributed")
+    rng = np.random.default_rng(11)
+    cases = [np.empty(0, np.int64), np.array([5]), np.arange(100, 100 + 262144), np.array([1, 2, 3, 7, 8, 20]),
+             np.unique(rng.integers(0, 5000, 1500)),
+             np.concatenate([np.arange(10, 500), np.arange(900, 1400)])]
+    for c in cases:
+        r = d.runs_of(c)
+        assert np.array_equal(d.cols_of(r), np.asarray(c, np.int64))
+        assert all(n >= 1 for _, n in r) and all(r[i][0] + r[i][1] < r[i + 1][0] for i in range(len(r) - 1))
+    assert d.runs_of(np.arange(100, 100 + 262144)) == [(100, 262144)]
