@@ -15,6 +15,7 @@
 #include "dia.cuh"
 #include "dia_tma.cuh"
 #include "grid.cuh"
+#include "host_util.h"
 #include "nccl_dyn.h"
 #include "pcg.cuh"
 #include "peer.cuh"
@@ -1058,19 +1059,9 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
     std::vector<int64_t> hd((size_t)nd);
     A_CUDA(cudaMemcpyAsync(hd.data(), d_dnodes, sizeof(int64_t) * (size_t)nd, cudaMemcpyDeviceToHost, st));
     A_CUDA(cudaStreamSynchronize(st));
-    std::vector<std::pair<int64_t, int>> pr((size_t)nd);
-    for (int64_t k = 0; k < nd; ++k) pr[(size_t)k] = {hd[(size_t)k] - 1, (int)k};
-    // (callers usually pass the Dirichlet nodes in ascending order already -- whole planes of a regular grid --
-    // and sorting half a million pairs costs tens of milliseconds per assembly on every rank)
-    if (!std::is_sorted(pr.begin(), pr.end())) std::sort(pr.begin(), pr.end());
     std::vector<int64_t> nodes;
     std::vector<int> slot;
-    nodes.reserve(pr.size());
-    slot.reserve(pr.size());
-    for (size_t k = 0; k < pr.size(); ++k) {
-      if (!nodes.empty() && nodes.back() == pr[k].first) slot.back() = pr[k].second;  // last duplicate wins
-      else { nodes.push_back(pr[k].first); slot.push_back(pr[k].second); }
-    }
+    dirichlet_table(hd, nodes, slot);  // sorted by node, last duplicate wins (host_util.h)
     nd_sorted = (int64_t)nodes.size();
     A_TRY(dalloc(h, &d_dsorted, nd_sorted));
     A_TRY(dalloc(h, &d_dsorted_slot, nd_sorted));
@@ -1147,8 +1138,7 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
   if (n_off) {
     h->halo_host.resize((size_t)n_off);
     A_CUDA(memcpy_sync(h->stream, h->halo_host.data(), d_refs, sizeof(int64_t) * (size_t)n_off, cudaMemcpyDeviceToHost));
-    std::sort(h->halo_host.begin(), h->halo_host.end());
-    h->halo_host.erase(std::unique(h->halo_host.begin(), h->halo_host.end()), h->halo_host.end());
+    sort_unique_i64(h->halo_host);  // ascending distinct columns (host_util.h: bitmap pass for dense planes)
     h->n_halo = (int64_t)h->halo_host.size();
     A_TRY(dalloc(h, &h->halo_glob, h->n_halo));
     A_CUDA(memcpy_sync(h->stream, h->halo_glob, h->halo_host.data(), sizeof(int64_t) * (size_t)h->n_halo, cudaMemcpyHostToDevice));

@@ -39,6 +39,21 @@ def test_device_arena_bookkeeping(tmp_path):
     assert r.returncode == 0 and "arena ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_host_util_helpers(tmp_path):
+    """csrc/host_util.h (sorted-unique of the halo references with a bitmap pass, the multi-rank Dirichlet table)
+    against the straightforward formulations, under ASan/UBSan."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path / "test_host_util")
+    subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "test_host_util.cpp")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "host_util ok" in r.stdout, r.stdout + r.stderr
+
+
 def _dia_tma_model_check(L, offs, unit, nf):
     """Replay, in numpy, what the producer lane of k_spmv_dia_tma copies for every interior tile and what the
     consumer threads read back (csrc/dia_tma.cuh), on the layout the library's own dia_tma_layout() produced.
