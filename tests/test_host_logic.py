@@ -430,3 +430,93 @@ def test_halo_plan_drives_a_correct_distributed_spmv(fv, orc, fourfractures, cas
         np.add.at(yl, loc.row, loc.data * vec[r][colmap])
         y[lo:hi] = yl
     assert np.allclose(y, A @ x, rtol=1e-12, atol=1e-14 * np.abs(A).max() * np.abs(x).max())
+
+
+def _dia_rank_emulation(A, lo, hi, halo, offs, s_global, x_global):
+    """numpy transcription of the per-rank index logic of csrc/dia.cuh for rows [lo, hi) of the global matrix A:
+    k_dia_fill (U_k[o+r] = A[r, r+o]; U_k[r] = A[r, r-o] only when the partner row is not owned), DiaDesc::xindex
+    (owned range, else the low / high halo run), k_dia_scale (S = U * (s_row * s_col)) and the row sum of
+    k_spmv_dia<UNIT> on the scaled copy.  `halo` = ascending global columns referenced off-rank."""
+    n = hi - lo
+    halo = np.asarray(halo, np.int64)
+    lo_run, hi_run = halo[halo < lo], halo[halo >= hi]
+    assert (lo_run.size == 0 or np.array_equal(lo_run, np.arange(lo_run[0], lo_run[0] + lo_run.size)))
+    assert (hi_run.size == 0 or np.array_equal(hi_run, np.arange(hi_run[0], hi_run[0] + hi_run.size)))
+    lo0 = int(lo_run[0]) if lo_run.size else 0
+    hi0 = int(hi_run[0]) if hi_run.size else 0
+    nlo = lo_run.size
+
+    def xindex(g):
+        l = g - lo
+        if 0 <= l < n:
+            return l
+        return n + (g - lo0) if g < lo else n + nlo + (g - hi0)
+
+    Ad = A.toarray()
+    U = [np.zeros(n + o) for o in offs]
+    for r in range(n):                                  # k_dia_fill
+        for k, o in enumerate(offs):
+            g = lo + r
+            if g + o < A.shape[0] and Ad[g, g + o] != 0.0:
+                U[k][o + r] = Ad[g, g + o]
+            if r < o and g - o >= 0 and Ad[g, g - o] != 0.0:
+                U[k][r] = Ad[g, g - o]
+    vec_s = np.concatenate([s_global[lo:hi], s_global[halo]])      # [owned | halo] after the halo exchange of s
+    vec_x = np.concatenate([x_global[lo:hi], x_global[halo]])
+    S = [np.zeros_like(u) for u in U]
+    for r in range(n):                                  # k_dia_scale
+        for k, o in enumerate(offs):
+            up = U[k][o + r]
+            if up != 0.0:
+                iu = r + o
+                S[k][o + r] = up * (vec_s[r] * vec_s[iu if iu < n else xindex(lo + iu)])
+            if r < o:
+                l = U[k][r]
+                S[k][r] = l * (vec_s[r] * vec_s[xindex(lo + r - o)]) if l != 0.0 else 0.0
+    y = np.zeros(n)
+    for r in range(n):                                  # k_spmv_dia<.., UNIT = true>
+        acc = 0.0
+        for k in range(len(offs) - 1, -1, -1):
+            o, l = offs[k], S[k][r]
+            if l != 0.0:
+                il = r - o
+                acc += l * (vec_x[il] if il >= 0 else vec_x[xindex(lo + il)])
+        acc += vec_x[r]
+        for k, o in enumerate(offs):
+            up = S[k][o + r]
+            if up != 0.0:
+                iu = r + o
+                acc += up * (vec_x[iu] if iu < n else vec_x[xindex(lo + iu)])
+        y[r] = acc
+    return y
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+def test_scaled_diagonal_format_across_slabs(fv, orc, world):
+    """The multi-rank layout of the Jacobi-scaled diagonal copy (symmetric storage with the partner's entries of the
+    first plane kept locally, halo runs below and above, scale factors of halo columns taken from the halo slots)
+    transcribed to numpy: every rank's rows of D^-1/2 A D^-1/2 x -- including middle ranks with neighbours on both
+    sides, which a 2-GPU box cannot exercise -- must equal the global product."""
+    import importlib
+    d = importlib.import_module("fvb200.distributed")
+    import scipy.sparse as sp
+    ns = [11, 4, 3]
+    _, nb, aol, _ = orc.regulargrid([0, 0, 0], [n - 1 for n in ns], ns, want_coords=False)
+    N, plane = int(np.prod(ns)), ns[1] * ns[2]
+    k = orc.nodehycos2neighborhycos(nb, np.random.default_rng(2).standard_normal(N), True)
+    dn = np.concatenate([np.arange(1, plane + 1), np.arange(N - plane + 1, N + 1)])
+    A = orc.assembleA(nb, aol, k, np.zeros(N), dn, np.zeros(dn.size), None, True).toscipy().tocsr()
+    nf = A.shape[0]
+    offs = [1, ns[2], plane]
+    s = 1.0 / np.sqrt(A.diagonal())
+    x = np.random.default_rng(3).standard_normal(nf)
+    want = (sp.diags(s) @ A @ sp.diags(s)) @ x
+    fn, _ = orc.getfreenodes(N, dn)
+    got = np.empty(nf)
+    for lo_p, hi_p in d.slab_planes(ns[0], world):
+        nlo, nhi = d.node_range_of_planes((lo_p, hi_p), ns[1], ns[2])
+        lo, hi = int(np.count_nonzero(fn[:nlo - 1])), int(np.count_nonzero(fn[:nhi]))
+        cols = np.unique(A[lo:hi].indices)
+        halo = cols[(cols < lo) | (cols >= hi)]
+        got[lo:hi] = _dia_rank_emulation(A, lo, hi, halo, offs, s, x)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-15 * np.abs(want).max())
