@@ -12,14 +12,14 @@ from ._lib import FVBError, LIB_PATH
 from .api import (ConvergenceHistory, DEFAULT_MAXITER, DeviceArray, SQRT_EPS, SparseMatrixCSC, System, assembleA, assembleb,
                   freenodes2nodes, getfreenodes, solvediffusion)
 from .grid import grid_sizes, nodehycos2neighborhycos, regulargrid
-from .transient import (adaptivebackwardeulerstep, adjointintegrate, backwardeulerintegrate,
-                        backwardeulerintegrate_generic, fixedbackwardeulerstep, getadjointfunctions,
+from .transient import (adaptivebackwardeulerstep, adjointintegrate, adjointintegrate_generic, backwardeulerintegrate,
+                        backwardeulerintegrate_generic, gradientintegrate_generic, fixedbackwardeulerstep, getadjointfunctions,
                         getcontinuoussolution, gradientintegrate, integrate_g, integratedfdplambda)
 
 __all__ = [
     "FVBError", "LIB_PATH", "DeviceArray", "ConvergenceHistory", "DEFAULT_MAXITER", "SQRT_EPS", "SparseMatrixCSC", "System",
     "assembleA", "assembleb", "freenodes2nodes", "getfreenodes", "solvediffusion", "grid_sizes",
     "nodehycos2neighborhycos", "regulargrid", "adaptivebackwardeulerstep", "adjointintegrate",
-    "backwardeulerintegrate", "backwardeulerintegrate_generic", "fixedbackwardeulerstep", "getadjointfunctions",
+    "backwardeulerintegrate", "backwardeulerintegrate_generic", "adjointintegrate_generic", "gradientintegrate_generic", "fixedbackwardeulerstep", "getadjointfunctions",
     "getcontinuoussolution", "gradientintegrate", "integrate_g", "integratedfdplambda", "jld",
 ]

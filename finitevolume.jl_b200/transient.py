@@ -244,6 +244,28 @@ def adjointintegrate(getdgdu, tspan, Ss, volumes, neighbors, areasoverlengths, c
         sysm.close()
 
 
+def adjointintegrate_generic(A, getdgdu, tspan, dt0=1.0, **kwargs):
+    """adjointintegrate(A, getdgdu, tspan; dt0, kwargs...) for a caller-supplied matrix (src/transient.jl:199-203;
+    test/odeadjoint.jl:36): integrates dgamma/dt = -A gamma + dg/du(T - t), gamma(0) = 0 with the generic
+    integrator (the solves are the caller's `linearsolver`) and returns (lambdas, ts_lambda), lambda(t) = gamma(T - t).
+    As in the reference, A is the matrix of the ADJOINT equation (pass the transpose of the forward one)."""
+    gamma0 = np.zeros(A.shape[1])
+    gammas, tsg = backwardeulerintegrate_generic(gamma0, A, lambda t: np.asarray(getdgdu(tspan[1] - t), np.float64), dt0,
+                                                 tspan[0], tspan[1], **kwargs)
+    return gammas[::-1], [tspan[1] - t for t in tsg][::-1]
+
+
+def gradientintegrate_generic(lambdac, du0dp, dgdp, dfdp, tspan, grids):
+    """gradientintegrate(lambdac::Function, du0dp, dgdp::Function, dfdp::Function, tspan) of src/transient.jl:207-216:
+    dG/dp = du0dp * lambda(0) + int dg/dp dt + int dfdp(t) * lambda(t) dt.  The reference integrates with adaptive
+    QuadGK; here `grids` (the time grids the piecewise-linear u and lambda live on) give a Simpson rule on the merged
+    grid, exact for products of two piecewise-linear functions."""
+    ts, ws = _simpson_nodes(grids, tspan[0], tspan[1])
+    i1 = sum(w * np.asarray(dgdp(t), np.float64) for t, w in zip(ts, ws))
+    i2 = sum(w * (np.asarray(dfdp(t), np.float64) @ np.asarray(lambdac(t), np.float64)) for t, w in zip(ts, ws))
+    return gradientintegrate(lambdac(tspan[0]), du0dp, i1, i2)
+
+
 # ======================================================================================================
 # Adjoint gradient: src/transientadjointutils.jl + gradientintegrate (src/transient.jl:207-216)
 # ======================================================================================================

@@ -278,6 +278,29 @@ def test_ode_controller_with_linearsolver_hook(fv):
         fv.backwardeulerintegrate_generic(np.ones(3), sp.diags(v).tocsr(), np.zeros(3), 1e-4, 0.0, 2.0)
 
 
+def test_odeadjoint_closed_form(fv):
+    """test/odeadjoint.jl:5-41 -- dx/dt = b x, x(0) = a, G = int x dt: forward solution, adjoint solution
+    lambda(t) = (1 - exp(b (T - t))) / b and the gradient [ (e^{bT}-1)/b, -a (e^{bT}-1)/b^2 + a T e^{bT}/b ],
+    all within the reference's rtol 1e-4, through the generic integrator / adjoint / gradient entry points with the
+    reference's own `linearsolver(A, b, x0) = A \\ b`."""
+    a, b, T = 1.0, 2.0, 1.0
+    A = np.array([[b]])
+    solver = lambda M, r, x0: np.linalg.solve(M, r)
+    xs, ts_x = fv.backwardeulerintegrate_generic(np.array([a]), -A, lambda t: np.zeros(1), 1e-5, 0.0, T, linearsolver=solver,
+                                                 atol=1e-8)
+    assert np.allclose(np.array(xs)[:, 0], a * np.exp(b * np.array(ts_x)), rtol=1e-4)
+    lambdas, ts_l = fv.adjointintegrate_generic(-A, lambda t: -np.ones(1), (0.0, T), dt0=1e-5, linearsolver=solver, atol=1e-8)
+    assert ts_l[0] == 0.0 and ts_l[-1] == T
+    assert np.allclose(np.array(lambdas)[:, 0], (1 - np.exp(b * (T - np.array(ts_l)))) / b, rtol=1e-4, atol=1e-9)
+    xc = fv.getcontinuoussolution(xs, ts_x)
+    lambdac = fv.getcontinuoussolution(lambdas, ts_l)
+    dx0dp = np.array([[-1.0], [0.0]])                                  # odeadjoint.jl:21-26
+    dfdp = lambda t: np.array([[0.0], [-xc(t)[0]]])                     # odeadjoint.jl:27-31
+    grad = fv.gradientintegrate_generic(lambdac, dx0dp, lambda t: np.zeros(2), dfdp, (0.0, T), [ts_x, ts_l])
+    exact = np.array([(math.exp(b * T) - 1) / b, -a / b ** 2 * (math.exp(b * T) - 1) + a / b * math.exp(b * T) * T])
+    assert np.allclose(grad, exact, rtol=1e-4)
+
+
 def test_controller_matches_oracle_trajectory(fv, orc):
     """The step-doubling controller (src/transient.jl:78-154) restated twice -- product host code
     vs oracle -- must take the same accepted steps when both use exact solves."""
