@@ -170,6 +170,12 @@ def cpu_reference_sample(n_s, sigma, rtol, target_n, target_iters=None):
     on this family grow linearly with n unless the GPU arm's count is given."""
     from oracle import fv_oracle as orc
     orc.build()
+    # all the host threads this process may use (torchrun presets OMP_NUM_THREADS=1 for its workers, which would
+    # silently turn the multi-rank launch of the reference arm into a single-threaded run)
+    try:
+        orc.set_num_threads(max(orc.num_threads(), len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        pass
     threads = orc.num_threads()
     ns = [n_s] * 3
     t0 = time.perf_counter()
