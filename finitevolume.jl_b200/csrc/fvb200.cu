@@ -299,10 +299,15 @@ int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot, 
   const int n = (int)h->nf_local;
   PeerRed pr = {nullptr, 0ull};
   int fin = h->nranks == 1 ? 1 : 0;
-  if (dot && fuse && n > 0) fin = red_mode(h, &pr);
+  if (dot && fuse) fin = red_mode(h, &pr);
   if (fin_out) *fin_out = fin;
-  if (n == 0) return FVB_OK;
-  const int grid = std::min(cdiv(n, kSpmvRows), h->num_sms * kSpmvCtasPerSm);
+  // A rank that owns no free row (e.g. a slab made of a Dirichlet plane only) still takes part in the
+  // reduction of u.Au with a zero contribution: the kernel runs with one CTA and no tiles.
+  if (n == 0 && !dot) {
+    if (h->nranks > 1 && h->peer && h->peer->active && vec == h->u) FVB_TRY(allreduce_fin(h, 0, FIN_NONE));  // see below
+    return FVB_OK;
+  }
+  const int grid = std::max(1, std::min(cdiv(n, kSpmvRows), h->num_sms * kSpmvCtasPerSm));
   const size_t smem = sizeof(SpmvSmem);
   int sample = -1;
   if (dot && h->prof_stride > 0 && h->prof_count < 64 && (h->prof_seen++ % h->prof_stride) == 0) {
@@ -344,6 +349,11 @@ int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot, 
                                                       h->partials, h->ticket, h->scal, fin, pr);
   if (sample >= 0) cudaEventRecord(h->prof_ev[2 * sample + 1], h->stream);
   h->tm.kernel_launches++;
+  // Peer-memory halo slots have no consumer->producer acknowledgement of their own: inside the CG loop the
+  // cross-rank reduction that follows every product orders "all ranks have read halo k" before "anybody pushes
+  // halo k+1".  A product that is NOT followed by a reduction (fvb_spmv, fvb_time_spmv, the warm-start residual)
+  // gets that ordering from an empty all-reduce, i.e. a barrier across the ranks on the device.
+  if (!dot && h->nranks > 1 && h->peer && h->peer->active && vec == h->u) FVB_TRY(allreduce_fin(h, 0, FIN_NONE));
   return FVB_OK;
 }
 
@@ -1233,10 +1243,18 @@ int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk
   FVB_TRY(dalloc(h, &d_err, ERR_COUNT));
   int init[ERR_COUNT];
   for (int &v : init) v = INT_MAX;
-  cudaMemcpyAsync(d_err, init, sizeof(init), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(d_cond, cond, sizeof(double) * (size_t)n_cond, cudaMemcpyDefault, st);
-  if (sources) cudaMemcpyAsync(h->sources, sources, sizeof(double) * (size_t)h->n_own_nodes, cudaMemcpyDefault, st);
-  if (dheads) cudaMemcpyAsync(h->dheads, dheads, sizeof(double) * (size_t)h->n_dirichlet, cudaMemcpyDefault, st);
+  {
+    cudaError_t ce = cudaMemcpyAsync(d_err, init, sizeof(init), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_cond, cond, sizeof(double) * (size_t)n_cond, cudaMemcpyDefault, st);
+    if (ce == cudaSuccess && sources)
+      ce = cudaMemcpyAsync(h->sources, sources, sizeof(double) * (size_t)h->n_own_nodes, cudaMemcpyDefault, st);
+    if (ce == cudaSuccess && dheads)
+      ce = cudaMemcpyAsync(h->dheads, dheads, sizeof(double) * (size_t)h->n_dirichlet, cudaMemcpyDefault, st);
+    if (ce != cudaSuccess) {
+      dfree(h, d_cond); dfree(h, d_err);
+      return set_error(FVB_ERR_CUDA, std::string("fvb_update_values upload: ") + cudaGetErrorString(ce));
+    }
+  }
   cudaEventRecord(h->ev[1], st);
   if (h->n_faces) {
     k_face_conductance<<<grid_for(h->n_faces), kBlock, 0, st>>>(h->n_faces, d_cond, n_cond, h->meta, h->aol, logk,
@@ -1250,13 +1268,18 @@ int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk
                                                            h->colidx, h->vals, h->diag, h->b, 0);
     h->tm.kernel_launches++;
   }
-  if (h->dia_on) build_dia(h, false);
-  if (h->mg && h->mg->ready) mg_setup(h, false);
+  h->logk = logk ? 1 : 0;  // the gradient gather picks dc = c (log K) or aol (plain K) from this
+  int st_dia = FVB_OK, st_mg = FVB_OK;
+  if (h->dia_on) st_dia = build_dia(h, false);
+  if (st_dia == FVB_OK && h->mg && h->mg->ready) st_mg = mg_setup(h, false);
   cudaEventRecord(h->ev[2], st);
   int herr[ERR_COUNT];
-  cudaMemcpyAsync(herr, d_err, sizeof(herr), cudaMemcpyDeviceToHost, st);
-  cudaError_t e = cudaStreamSynchronize(st);
+  cudaError_t e = cudaMemcpyAsync(herr, d_err, sizeof(herr), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
   dfree(h, d_cond); dfree(h, d_err);
+  if (st_dia != FVB_OK) return st_dia;
+  if (st_mg != FVB_OK) return st_mg;
   if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->tm.assemble_ms = ms;

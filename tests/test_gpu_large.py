@@ -1,7 +1,9 @@
-"""BASELINE config 2 at full size (256^3 lognormal, single B200; 16.6 M unknowns, 116 M nonzeros) through
-size-independent properties -- the oracle cannot assemble/solve this in test time:
+"""BASELINE config 2 at full size (256^3 lognormal, single B200; 16.6 M unknowns, 116 M nonzeros): a direct
+comparison with the CPU oracle (structure bit-exact, values <= 1e-14, heads <= 1e-8 at rtol 1e-12 on both sides;
+the threaded oracle needs about a minute) and size-independent properties:
 determinism, symmetry, row sums, the counts of SURVEY 8a, residual of the returned heads, maximum principle,
 linearity in the Dirichlet data, agreement of both SpMV formats and both preconditioners, slab rows == whole rows."""
+import os
 import ctypes
 import math
 
@@ -52,6 +54,40 @@ def test_counts_and_determinism(fv, big):
     # b is exactly that coupling times head 1 on the left plane, 0 elsewhere
     b = s.b()
     assert np.allclose(b[:pl], rs[:pl], rtol=1e-13) and not b[pl:].any()
+
+
+def test_oracle_parity_256(fv, orc, big):
+    """north_star's correctness bar at BASELINE config 2: CSR structure bit-exact, assembled values within 1e-14
+    relative, heads within 1e-8 relative at matched residual tolerance (1e-12), against the oracle's serial
+    restatement of src/FiniteVolume.jl:75-165 on the same seeded inputs."""
+    n, N, s = big["n"], big["N"], big["s"]
+    try:
+        orc.set_num_threads(max(orc.num_threads(), len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        pass
+    _, nb, aol, _ = orc.regulargrid([0, 0, 0], [n - 1] * 3, [n, n, n], want_coords=False)
+    kf = orc.nodehycos2neighborhycos(nb, big["lnk"], True)
+    # the device-side grid helpers produced the very same inputs
+    assert np.array_equal(big["kf"].to_host(), kf) and np.array_equal(big["aol"].to_host(), aol)
+    Ao = orc.assembleA(nb, aol, kf, big["src"], big["dn"], big["dh"], None, True)
+    bo = orc.assembleb(nb, aol, kf, big["src"], big["dn"], big["dh"], None, True)
+    p, i, v = s.csr()
+    assert np.array_equal(p, Ao.colptr) and np.array_equal(i, Ao.rowval)           # structure: bit-exact
+    assert np.max(np.abs(v - Ao.nzval) / np.abs(Ao.nzval)) <= 1e-14                # values (log K: exp <= 1 ulp)
+    b = s.b()
+    assert np.max(np.abs(b - bo)) <= 1e-14 * np.max(np.abs(bo))
+    del nb, aol, kf, p, i, v
+    xo, cho = orc.cg(Ao, bo, Pl="jacobi", tol=1e-12, maxiter=100000, threaded=True)
+    ho, _, _ = orc.freenodes2nodes(xo, big["src"], big["dn"], big["dh"])
+    head, _, ch = s.solve(rtol=1e-12)
+    assert ch.isconverged and cho.isconverged
+    assert np.max(np.abs(head - ho)) <= 1e-8 * np.max(np.abs(ho))                  # heads at matched tolerance
+    assert abs(ch.iters - cho.iters) <= max(5, cho.iters // 100)
+    # the multigrid-preconditioned solve meets the same bar
+    s.set_preconditioner("mg")
+    head_mg, _, ch_mg = s.solve(rtol=1e-12)
+    s.set_preconditioner("jacobi")
+    assert ch_mg.isconverged and np.max(np.abs(head_mg - ho)) <= 1e-8 * np.max(np.abs(ho))
 
 
 def test_symmetry_and_formats(fv, big):

@@ -50,6 +50,16 @@ def _worker(rank, world, port, q):
     d.init_comm(s)
     plan = d.exchange_halo_plan(s)
     assert plan[0] == s.plan[0]
+    # same partition again: the cached plan (fixed-size record path) must be identical
+    plan2 = d.exchange_halo_plan(s)
+    assert plan2[0] == plan[0] and plan2[1] == plan[1] and np.array_equal(plan2[2], plan[2]) and plan2[3] == plan[3]
+    # a halo with more than two runs on one rank sends every rank down the pickled-object path
+    class Ragged(StubSystem):
+        def halo_cols(self):
+            return np.array([self.n + 1, self.n + 3, self.n + 5] if self.rank == 0 else [self.n], np.int64)
+    s3 = Ragged(rank, 6)
+    plan3 = d.exchange_halo_plan(s3)
+    assert plan3[3] == ([3] if rank == 0 else [1]) and plan3[1] == ([1] if rank == 0 else [3])
     q.put((rank, s.plan[0], s.plan[1], s.plan[2].tolist(), s.plan[3], s.uid[2] == bytes(range(128)), s.uid[:2]))
     dist.barrier()
     dist.destroy_process_group()
