@@ -55,6 +55,11 @@ def parse():
     ap.add_argument("--cpu-sample-n", type=int, default=192, help="grid size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--implicit", action="store_true",
+                    help="grid-implicit inputs: upload node ln K only and assemble with fvb_assemble_regulargrid (no per-face "
+                         "array exists anywhere); the only way to run --grid 1024 on 1-2 GPUs")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs (device-grid e2e, other preconditioner, CSR kernel timing, tight tolerance)")
     ap.add_argument("--parity-n", type=int, default=96,
                     help="grid size of the oracle parity leg run after the timed region at every N (0: skip)")
     ap.add_argument("--tight-rtol", type=float, default=1e-12,
@@ -110,6 +115,32 @@ def problem_inputs(fv, n, sigma, planes=None, pin=None):
     dh[plane:] = 0.0
     return dict(N=N, F=F, node_range=(lo, hi), nb=nb, aol=aol, kf=kf, src=src, dn=dn, dh=dh, lnk_slab=lnk_slab,
                 lnk_node_lo=k_lo)
+
+
+def implicit_inputs(n, sigma, planes, pin):
+    """The same workload described by node values only: ln K of the owned x-planes plus one plane on each side
+    (what fvb_assemble_regulargrid takes), the two Dirichlet planes, zero sources (passed as NULL)."""
+    N, plane = n ** 3, n * n
+    lo, hi = (planes[0] - 1) * plane + 1, planes[1] * plane
+    k_lo, k_hi = max(1, lo - plane), min(N, hi + plane)
+    lnk_slab = pin((k_hi - k_lo + 1,), np.float64)
+    rng = np.random.default_rng(0)
+    # the global field is drawn in node order from one stream (same numbers as problem_inputs); stream through it
+    chunk, pos = 1 << 24, 0
+    while pos < k_hi:
+        m = min(chunk, N - pos)
+        z = rng.standard_normal(m)
+        a, b = max(pos, k_lo - 1), min(pos + m, k_hi)
+        if a < b:
+            lnk_slab[a - (k_lo - 1):b - (k_lo - 1)] = math.log(1e-5) + sigma * z[a - pos:b - pos]
+        pos += m
+    dn = pin((2 * plane,), np.int64)
+    dn[:plane] = np.arange(1, plane + 1)
+    dn[plane:] = np.arange(N - plane + 1, N + 1)
+    dh = pin((2 * plane,), np.float64)
+    dh[:plane] = 1.0
+    dh[plane:] = 0.0
+    return dict(N=N, F=0, node_range=(lo, hi), lnk_slab=lnk_slab, lnk_node_lo=k_lo, dn=dn, dh=dh)
 
 
 def spmv_bytes(nf, nnz):
@@ -433,15 +464,21 @@ def main():
         return t.numpy()
     pinned.keep = []
 
+    implicit = bool(args.implicit)
     t_gen = time.perf_counter()
-    P = problem_inputs(fv, n, args.sigma, planes=mine, pin=pinned)
+    if implicit:
+        P = implicit_inputs(n, args.sigma, mine, pinned)
+        in_keys = ("lnk_slab", "dn", "dh")
+    else:
+        P = problem_inputs(fv, n, args.sigma, planes=mine, pin=pinned)
+        in_keys = ("nb", "aol", "kf", "src", "dn", "dh")
     t_gen = time.perf_counter() - t_gen
     lo, hi = P["node_range"]
-    h2d_bytes = sum(P[k].nbytes for k in ("nb", "aol", "kf", "src", "dn", "dh"))
+    h2d_bytes = sum(P[k].nbytes for k in in_keys)
     d2h_bytes = (hi - lo + 1) * 8
 
     # device-resident copies for the `value` leg
-    dev = {k: torch.from_numpy(P[k]).cuda(non_blocking=True) for k in ("nb", "aol", "kf", "src", "dn", "dh")}
+    dev = {k: torch.from_numpy(P[k]).cuda(non_blocking=True) for k in in_keys}
     head_dev = torch.empty(hi - lo + 1, dtype=torch.float64, device="cuda")
     head_host = torch.empty(hi - lo + 1, dtype=torch.float64, pin_memory=True)
     torch.cuda.synchronize()
@@ -463,11 +500,19 @@ def main():
 
     wall_parts = {}
 
+    def assemble_from(a):
+        """One assembly from the addresses in `a` (device-resident copies or pinned host buffers)."""
+        if implicit:
+            sysm.assemble_regulargrid([0, 0, 0], [n - 1] * 3, [n, n, n], a["lnk_slab"], None, P["dn"], P["dh"],
+                                      logmean=True, logtransformconductivity=True, planes=mine)
+        else:
+            sysm.assemble_raw(P["N"], lo, hi, P["F"], a["nb"], a["aol"], a["kf"], P["F"], 0, True, a["src"],
+                              P["dn"].size, a["dn"], a["dh"])
+
     def step(src_arrays, head_ptr):
         a = src_arrays
         t0 = time.perf_counter()
-        sysm.assemble_raw(P["N"], lo, hi, P["F"], a["nb"], a["aol"], a["kf"], P["F"], 0, True, a["src"],
-                          P["dn"].size, a["dn"], a["dh"])
+        assemble_from(a)
         t1 = time.perf_counter()
         if world > 1:
             fvd.exchange_halo_plan(sysm)
@@ -495,7 +540,7 @@ def main():
         return r
 
     dev_ptrs = {k: v.data_ptr() for k, v in dev.items()}
-    host_ptrs = {k: P[k].ctypes.data for k in ("nb", "aol", "kf", "src", "dn", "dh")}
+    host_ptrs = {k: P[k].ctypes.data for k in in_keys}
 
     def maxreduce(x):
         if world == 1:
@@ -546,17 +591,40 @@ def main():
     e2e_parts = dict(wall_parts)
     # ---- end to end with the device-side grid generator (extra information) ---------------------
     head_e2e = head_host.numpy().copy()
-    step_devgrid(head_host.data_ptr())  # warm-up of the extra allocations
-    barrier()
-    g0 = time.perf_counter()
-    it_g, conv_g = step_devgrid(head_host.data_ptr())
-    barrier()
-    devgrid = {"value": maxreduce(time.perf_counter() - g0), "unit": "s", "pcg_iterations": it_g,
-               "h2d_bytes_per_step": int(P["lnk_slab"].nbytes + P["src"].nbytes + P["dn"].nbytes + P["dh"].nbytes),
-               "identical_heads": bool(np.array_equal(head_host.numpy(), head_e2e)), "host_wall": dict(wall_parts),
-               "solve_ms": sysm.timings()["solve_ms"], "assemble_ms": sysm.timings()["assemble_ms"],
-               "format": list(sysm.spmv_format()),
-               "note": "host uploads node ln K only; neighbors/areasoverlengths/face K generated on the device"}
+    assembly_kind = sysm.assembly()  # "box": closed-form rows from the caller's arrays; "implicit": no face arrays
+    extras = not args.no_extras
+    devgrid, implicit_leg = None, None
+    if extras and not implicit:
+        step_devgrid(head_host.data_ptr())  # warm-up of the extra allocations
+        barrier()
+        g0 = time.perf_counter()
+        it_g, conv_g = step_devgrid(head_host.data_ptr())
+        barrier()
+        devgrid = {"value": maxreduce(time.perf_counter() - g0), "unit": "s", "pcg_iterations": it_g,
+                   "h2d_bytes_per_step": int(P["lnk_slab"].nbytes + P["src"].nbytes + P["dn"].nbytes + P["dh"].nbytes),
+                   "identical_heads": bool(np.array_equal(head_host.numpy(), head_e2e)), "host_wall": dict(wall_parts),
+                   "solve_ms": sysm.timings()["solve_ms"], "assemble_ms": sysm.timings()["assemble_ms"],
+                   "format": list(sysm.spmv_format()), "assembly": sysm.assembly(),
+                   "note": "host uploads node ln K only; neighbors/areasoverlengths/face K generated on the device"}
+        # the same problem with no face array at all (fvb_assemble_regulargrid)
+        def step_implicit(head_ptr):
+            sysm.assemble_regulargrid([0, 0, 0], [n - 1] * 3, [n, n, n], P["lnk_slab"].ctypes.data, None, P["dn"], P["dh"],
+                                      logmean=True, logtransformconductivity=True, planes=mine)
+            if world > 1:
+                fvd.exchange_halo_plan(sysm)
+            return sysm.solve_raw(args.rtol, args.maxiter, head_ptr=head_ptr)
+        step_implicit(head_host.data_ptr())
+        barrier()
+        g0 = time.perf_counter()
+        it_i, conv_i = step_implicit(head_host.data_ptr())
+        barrier()
+        implicit_leg = {"value": maxreduce(time.perf_counter() - g0), "unit": "s", "pcg_iterations": it_i,
+                        "h2d_bytes_per_step": int(P["lnk_slab"].nbytes + P["dn"].nbytes + P["dh"].nbytes),
+                        "identical_heads": bool(np.array_equal(head_host.numpy(), head_e2e)),
+                        "solve_ms": sysm.timings()["solve_ms"], "assemble_ms": sysm.timings()["assemble_ms"],
+                        "assembly": sysm.assembly(),
+                        "note": "grid-implicit assembly: no neighbors/areasoverlengths/conductivities array exists, "
+                                "rows computed from node ln K and the grid spacing"}
 
     # ---- the other preconditioner on the same resident inputs (extra information, not the headline) ----
     alt = "mg" if args.precond == "jacobi" else "jacobi"
@@ -564,8 +632,10 @@ def main():
     # The distributed V-cycle has been exercised on 1 and 2 GPUs only (tests/test_gpu_multi.py needs the GPUs it
     # names); an extra-information leg must not be able to stall a 4- or 8-rank headline run in a collective,
     # so beyond 2 ranks it runs on request only.
-    run_alt = world <= 2 or os.environ.get("FVB_BENCH_ALT", "0") == "1"
+    run_alt = extras and (world <= 2 or os.environ.get("FVB_BENCH_ALT", "0") == "1")
     try:
+        if not extras:
+            raise RuntimeError("skipped (--no-extras)")
         if not run_alt:
             raise RuntimeError("skipped beyond 2 ranks (set FVB_BENCH_ALT=1 to run it)")
         head_main = head_host.numpy().copy()
@@ -584,10 +654,12 @@ def main():
         ea = maxreduce(time.perf_counter() - ea)
         tma = sysm.timings()
         barrier()
-        eg = time.perf_counter()
-        step_devgrid(head_host.data_ptr())
-        barrier()
-        eg = maxreduce(time.perf_counter() - eg)
+        eg = None
+        if not implicit:
+            eg = time.perf_counter()
+            step_devgrid(head_host.data_ptr())
+            barrier()
+            eg = maxreduce(time.perf_counter() - eg)
         diff = float(np.max(np.abs(head_host.numpy() - head_main)))
         alt_info = {"precond": alt, "active": sysm.preconditioner()[0], "value": maxreduce(a_ms / args.steps / 1e3),
                     "unit": "s", "e2e": ea, "e2e_device_grid": eg, "pcg_iterations": it_a, "converged": bool(conv_a),
@@ -602,13 +674,12 @@ def main():
     # ---- time-to-solution at the parity tolerance (report timing at sqrt(eps) AND at the tolerance
     #      where "heads within 1e-8" is a meaningful statement), same resident inputs ---------------------------
     tight = None
-    if args.tight_rtol and args.tight_rtol > 0:
+    if extras and args.tight_rtol and args.tight_rtol > 0:
         try:
             head_tj = torch.empty(hi - lo + 1, dtype=torch.float64, pin_memory=True)
             sysm.set_preconditioner("jacobi")
             barrier()
-            sysm.assemble_raw(P["N"], lo, hi, P["F"], dev_ptrs["nb"], dev_ptrs["aol"], dev_ptrs["kf"], P["F"], 0, True,
-                              dev_ptrs["src"], P["dn"].size, dev_ptrs["dn"], dev_ptrs["dh"])
+            assemble_from(dev_ptrs)
             if world > 1:
                 fvd.exchange_halo_plan(sysm)
             it_t, conv_t = sysm.solve_raw(args.tight_rtol, args.maxiter, head_ptr=head_tj.data_ptr())
@@ -622,8 +693,7 @@ def main():
             if run_alt:
                 head_tm = torch.empty(hi - lo + 1, dtype=torch.float64, pin_memory=True)
                 sysm.set_preconditioner("mg")
-                sysm.assemble_raw(P["N"], lo, hi, P["F"], dev_ptrs["nb"], dev_ptrs["aol"], dev_ptrs["kf"], P["F"], 0, True,
-                                  dev_ptrs["src"], P["dn"].size, dev_ptrs["dn"], dev_ptrs["dh"])
+                assemble_from(dev_ptrs)
                 if world > 1:
                     fvd.exchange_halo_plan(sysm)
                 it_m, conv_m = sysm.solve_raw(args.tight_rtol, args.maxiter, head_ptr=head_tm.data_ptr())
@@ -672,7 +742,7 @@ def main():
 
     # the general CSR kernel on the same resident matrix, timed alone (20 launches, CUDA events)
     csr_roof = None
-    if world == 1:
+    if world == 1 and extras and sz["nnz_local"] < 2 ** 31 - 64:
         sysm.set_spmv_format(1)
         ms_csr = sysm.time_spmv(warmup=3, reps=20)
         sysm.set_spmv_format(0)
@@ -704,12 +774,16 @@ def main():
             "metric": "steady_solvediffusion_time", "value": step_s, "unit": "s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": dict(workload_config(args, world),
+                           inputs=("grid-implicit: node ln K + grid spacing only (fvb_assemble_regulargrid)" if implicit else
+                                   "the reference's per-face arrays: neighbors, areasoverlengths, conductivities (fvb_assemble)")),
             "clocks": clocks,
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "h2d_ms": e2e_tm["h2d_ms"], "assemble_ms": e2e_tm["assemble_ms"], "solve_ms": e2e_tm["solve_ms"],
                     "d2h_ms": e2e_tm["d2h_ms"], "pcg_iterations": it_e, "host_wall": e2e_parts},
             "e2e_device_grid": devgrid,
+            "e2e_implicit_grid": implicit_leg,
+            "assembly": assembly_kind,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm",
                          "kernel": ("%s<true,%d,%s> (symmetric-diagonal SpMV%s + fused u.Au)"

@@ -23,6 +23,7 @@ SYMBOLS = [
     "fvb_vec_download", "fvb_vec_copy", "fvb_vec_load_b", "fvb_vec_diffnorm", "fvb_set_storage",
     "fvb_step", "fvb_vec_to_nodes", "fvb_time_spmv", "fvb_device_alloc", "fvb_device_free", "fvb_device_copy", "fvb_regulargrid",
     "fvb_nodehycos2neighborhycos", "fvb_set_preconditioner", "fvb_get_preconditioner", "fvb_set_spmv_format", "fvb_get_spmv_format", "fvb_set_pcg_scaling", "fvb_get_pcg_scaling", "fvb_set_profiling", "fvb_get_timings", "fvb_sync",
+    "fvb_set_assembly", "fvb_get_assembly", "fvb_assemble_regulargrid",
 ]
 
 

@@ -204,6 +204,37 @@ class System:
                                                 C.c_int(int(bool(logtransformhyco))), C.c_void_p(out.ptr)))
         return out
 
+    def assemble_regulargrid(self, mins, maxs, ns, nodehycos, sources, dirichletnodes, dirichletheads,
+                             logmean=True, logtransformconductivity=True, planes=None):
+        """Grid-implicit assembly (fvb_assemble_regulargrid): regulargrid + nodehycos2neighborhycos + assembleA/b
+        without any per-face array.  nodehycos: node values (node order) of planes max(1,lo-1)..min(n1,hi+1)
+        (numpy, a DeviceArray or an int device address); sources: owned nodes or None (zeros)."""
+        mn, mx, nn = f64(mins), f64(maxs), i64(ns)
+        lo, hi = (1, int(nn[0])) if planes is None else (int(planes[0]), int(planes[1]))
+        if isinstance(nodehycos, int):
+            k_p, keep_k = C.c_void_p(nodehycos), None
+        else:
+            k_p, _, keep_k = _arg(nodehycos, np.float64)
+        src_p, keep_s = (None, None) if sources is None else _arg(sources, np.float64)[::2]
+        dn, dh = i64(dirichletnodes), f64(dirichletheads)
+        check(lib().fvb_assemble_regulargrid(self._h, ptr(mn), ptr(mx), ptr(nn), C.c_int64(lo), C.c_int64(hi), k_p,
+                                             C.c_int(int(bool(logmean))), C.c_int(int(bool(logtransformconductivity))),
+                                             src_p, C.c_int64(dn.size), ptr(dn), ptr(dh)))
+        plane = int(nn[1]) * int(nn[2])
+        self.node_lo, self.node_hi = (lo - 1) * plane + 1, hi * plane
+        self._logk = bool(logtransformconductivity)
+        return self
+
+    def set_assembly(self, mode):
+        """0 = automatic (closed-form rows for regulargrid-ordered face lists), 1 = always the general path."""
+        check(lib().fvb_set_assembly(self._h, C.c_int(int(mode))))
+
+    def assembly(self):
+        """-> "general" | "box" (closed form from the caller's arrays) | "implicit" (no face arrays)."""
+        a = C.c_int()
+        check(lib().fvb_get_assembly(self._h, C.byref(a)))
+        return {0: "general", 1: "box", 2: "implicit"}[a.value]
+
     def update_values(self, conductivities, sources=None, dirichletheads=None, logtransformconductivity=None):
         cond = f64(conductivities)
         logk = self._logk if logtransformconductivity is None else bool(logtransformconductivity)

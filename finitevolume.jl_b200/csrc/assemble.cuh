@@ -36,7 +36,7 @@ __global__ void k_mark_dirichlet(const int64_t *__restrict__ dnodes, int64_t nd,
   if (node < 0 || node >= n_nodes) { atomicMin(&err[ERR_BAD_NODE], (int)min((int64_t)INT_MAX - 1, k)); return; }
   if (node < node_lo || node >= node_hi) return;
   atomicMax(&dslot[node - node_lo], (int)k);
-  if (sources[node - node_lo] != 0.0) atomicMin(&err[ERR_SRC_ON_DIRICHLET], (int)k);
+  if (sources && sources[node - node_lo] != 0.0) atomicMin(&err[ERR_SRC_ON_DIRICHLET], (int)k);
 }
 
 // flag[i] = 1 for free nodes (input of the scan).

@@ -43,6 +43,7 @@ struct PcgScal {
 };
 
 class Arena;      // arena.h
+struct BoxDesc;   // box.cuh
 struct Comm;      // nccl_dyn.h
 struct PeerState; // fvb200.cu (peer.cuh tables)
 struct MgState;   // fvb200.cu (mg.cuh hierarchy)
@@ -116,6 +117,19 @@ struct fvb_handle_s {
   int64_t dia_off[4] = {};
   double *dia_U[4] = {};
   int64_t dia_lo0 = 0, dia_nlo = 0, dia_hi0 = 0, dia_nhi = 0;
+
+  // closed-form assembly of regulargrid-ordered problems straight into the diagonal copy (box.cuh)
+  int box_request = 0;          // 0 automatic, 1 never (FVB_BOX=0): always the general adjacency/CSR path
+  bool box = false;             // current problem assembled by the box path: no adjacency, CSR built lazily
+  bool box_implicit = false;    // ... from node conductivities and the grid spacing only (no face arrays at all)
+  fvb::BoxDesc *boxd = nullptr;
+  uint8_t *boxmask = nullptr;   // [nf_local] which of the six off-diagonal entries each row stores
+  double *nodek = nullptr;      // implicit: node conductivities, nodes nodek_lo .. (planes p_lo-1 .. p_hi+1)
+  int64_t nodek_n = 0, nodek_ofs = 0;  // entries held; index of local node 0
+  int box_logmean = 0;
+  int64_t *d_dsorted = nullptr; // sorted Dirichlet table of the whole problem (slab ranks; retained in box mode)
+  int32_t *d_dsorted_slot = nullptr;
+  int64_t nd_sorted = 0;
 
   // symmetric Jacobi scaling of that copy (dia.cuh: k_dia_scale; pcg.cuh: SC kernels)
   int scale_request = 0;        // 0 auto, 1 never

@@ -11,6 +11,7 @@
 
 #include "arena.h"
 #include "assemble.cuh"
+#include "box.cuh"
 #include "common.cuh"
 #include "dia.cuh"
 #include "dia_tma.cuh"
@@ -112,6 +113,8 @@ cudaError_t memcpy_sync(cudaStream_t st, void *dst, const void *src, size_t byte
   return e != cudaSuccess ? e : cudaStreamSynchronize(st);
 }
 
+int ensure_csr(fvb_handle h);  // box problems: CSR image on first demand (defined with the box code below)
+
 int grid_for(int64_t n) { return std::max(1, cdiv(n, kBlock)); }
 int vgrid(fvb_handle h, int64_t n) { return std::max(1, std::min(cdiv(n, kBlock), h->num_sms * 8)); }
 
@@ -129,6 +132,10 @@ void free_problem(fvb_handle h) {
   for (auto &u : h->dia_U) dfree(h, u);
   for (auto &u : h->dia_S) dfree(h, u);
   dfree(h, h->sinv);
+  dfree(h, h->boxmask); dfree(h, h->nodek); dfree(h, h->d_dsorted); dfree(h, h->d_dsorted_slot);
+  delete h->boxd;
+  h->boxd = nullptr;
+  h->box = false; h->box_implicit = false; h->nodek_n = 0; h->nd_sorted = 0;
   h->scale_state = 0;
   h->dia_on = false;
   h->dia_K = 0;
@@ -157,7 +164,8 @@ int ensure_workspace(fvb_handle h) {
   const int64_t n = h->nf_local;
   if (!h->x) {
     FVB_TRY(dalloc(h, &h->x, n)); FVB_TRY(dalloc(h, &h->r, n)); FVB_TRY(dalloc(h, &h->c, n));
-    FVB_TRY(dalloc(h, &h->dinv, n)); FVB_TRY(dalloc(h, &h->rhs, n));
+    // dinv (unscaled recurrence, multigrid PCG) and rhs (transient step) are taken on first use: the scaled
+    // steady solve needs neither, and at 1024^3 on one GPU each is 8.6 GB
     if (h->nranks == 1) {
       FVB_TRY(dalloc(h, &h->u, n + h->n_halo));
     } else if (h->u_cap < n + h->n_halo) {
@@ -295,6 +303,7 @@ bool use_dia_tma(fvb_handle h, const double *vec, const DiaTmaLayout &L, bool sc
 // must then skip allreduce_fin: *fin_out reports the finalize mode used).
 int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot, bool scaled = false, bool fuse = false,
                 int *fin_out = nullptr) {
+  if (h->box && h->fmt_request == 1) FVB_TRY(ensure_csr(h));  // forced CSR on a problem assembled without one
   FVB_TRY(halo_exchange(h, vec));
   const int n = (int)h->nf_local;
   PeerRed pr = {nullptr, 0ull};
@@ -341,6 +350,8 @@ int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot, 
 #undef FVB_DIA_LAUNCH
   } else if (scaled)
     return set_error(FVB_ERR_STATE, "scaled SpMV requested without the diagonal format");
+  else if (h->box && !h->rowptr)
+    return set_error(FVB_ERR_STATE, "internal: CSR product requested before ensure_csr");
   else if (dot)
     k_spmv<true><<<grid, kSpmvThreads, smem, h->stream>>>(n, h->rowptr, h->colidx, h->vals, vec, out, h->Dvec, sigma,
                                                      h->partials, h->ticket, h->scal, fin, pr);
@@ -505,6 +516,196 @@ int build_scaled(fvb_handle h) {
   }
   h->tm.kernel_launches++;
   h->scale_state = 1;
+  return FVB_OK;
+}
+
+// ---- closed-form assembly of regulargrid-ordered problems (box.cuh) -------------------------------------------------
+// Number of faces regulargrid lists for the x-planes p_lo..p_hi (plus the +x faces of plane p_lo-1).
+int64_t box_face_count(const GridDesc &G) {
+  const int64_t plane = G.n2 * G.n3, pfull = plane + (G.n2 - 1) * G.n3 + G.n2 * (G.n3 - 1);
+  int64_t F = G.e_lo < G.p_lo ? plane : 0;
+  const int64_t full = std::max<int64_t>(0, std::min<int64_t>(G.p_hi, G.n1 - 1) - G.p_lo + 1);
+  F += full * pfull;
+  if (G.p_hi == G.n1) F += pfull - plane;
+  return F;
+}
+
+// Rows of the current box problem: (re)compute U, diag, b, the entry masks and nnz from the retained inputs.
+int box_fill(fvb_handle h) {
+  cudaStream_t st = h->stream;
+  const BoxDesc &B = *h->boxd;
+  const int64_t n = h->nf_local;
+  h->scale_state = 0;  // values change: the Jacobi-scaled copy is stale
+  unsigned long long *d_nnz = nullptr;
+  FVB_TRY(dalloc(h, &d_nnz, 1));
+  FVB_CUDA(cudaMemsetAsync(d_nnz, 0, sizeof(unsigned long long), st));
+  for (int k = 0; k < 3; ++k)  // lower entries without an owned partner row: zero unless the rank below owns it
+    FVB_CUDA(cudaMemsetAsync(h->dia_U[k], 0, sizeof(double) * (size_t)h->dia_off[k], st));
+  const int g = std::max(1, std::min(cdiv(B.n_own, kBlock), h->num_sms * 16));
+  if (h->box_implicit) {
+    FaceImplicit fc{h->nodek, h->nodek_ofs, h->box_logmean, h->logk};
+    k_box_values<<<g, kBlock, 0, st>>>(B, fc, h->nodemap, h->sources, h->dheads, h->d_dsorted, h->d_dsorted_slot,
+                                       h->nd_sorted, h->dia_U[0], h->dia_U[1], h->dia_U[2], h->diag, h->b, h->boxmask, d_nnz);
+  } else {
+    FaceFromArray fc{h->cface};
+    k_box_values<<<g, kBlock, 0, st>>>(B, fc, h->nodemap, h->sources, h->dheads, h->d_dsorted, h->d_dsorted_slot,
+                                       h->nd_sorted, h->dia_U[0], h->dia_U[1], h->dia_U[2], h->diag, h->b, h->boxmask, d_nnz);
+  }
+  h->tm.kernel_launches++;
+  unsigned long long nnz = 0;
+  cudaError_t e = memcpy_sync(st, &nnz, d_nnz, sizeof(nnz), cudaMemcpyDeviceToHost);
+  dfree(h, d_nnz);
+  if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, std::string("box assembly: ") + cudaGetErrorString(e));
+  h->nnz = (int64_t)nnz;
+  (void)n;
+  return FVB_OK;
+}
+
+// Plane just outside the owned range: 0 none, 1 entirely free, 2 entirely Dirichlet, -1 mixed.
+// `nodes` = ascending distinct 0-based Dirichlet nodes of the whole problem.
+int box_plane_kind(const std::vector<int64_t> &nodes, int64_t first, int64_t plane) {
+  const int64_t c = std::lower_bound(nodes.begin(), nodes.end(), first + plane) - std::lower_bound(nodes.begin(), nodes.end(), first);
+  return c == 0 ? 1 : (c == plane ? 2 : -1);
+}
+
+// Allocate the diagonal copy for a verified box problem, install halo runs and fill the rows.
+// On FVB_OK with *ok == false nothing was kept (not enough memory for this path's arrays is an error, not a fallback).
+int box_install(fvb_handle h, const BoxDesc &B) {
+  cudaStream_t st = h->stream;
+  const int64_t n = h->nf_local, plane = B.G.n2 * B.G.n3;
+  const int64_t o[3] = {1, B.G.n3, plane};
+  delete h->boxd;
+  h->boxd = new BoxDesc(B);
+  for (int k = 0; k < 3; ++k) {
+    FVB_TRY(dalloc(h, &h->dia_U[k], n + o[k]));
+    h->dia_off[k] = o[k];
+  }
+  h->dia_off[3] = 0;
+  h->dia_K = 3;
+  FVB_TRY(dalloc(h, &h->diag, n));
+  FVB_TRY(dalloc(h, &h->b, n));
+  FVB_TRY(dalloc(h, &h->boxmask, n));
+  // halo: whole planes of the neighbouring ranks, contiguous in the global free numbering
+  h->dia_lo0 = h->dia_hi0 = 0; h->dia_nlo = h->dia_nhi = 0;
+  h->halo_host.clear();
+  if (B.lo_kind == 1) { h->dia_lo0 = h->row_start - plane; h->dia_nlo = plane; }
+  if (B.hi_kind == 1) { h->dia_hi0 = h->row_start + n; h->dia_nhi = plane; }
+  h->n_halo = h->dia_nlo + h->dia_nhi;
+  if (h->n_halo) {
+    h->halo_host.resize((size_t)h->n_halo);
+    for (int64_t i = 0; i < h->dia_nlo; ++i) h->halo_host[(size_t)i] = h->dia_lo0 + i;
+    for (int64_t i = 0; i < h->dia_nhi; ++i) h->halo_host[(size_t)(h->dia_nlo + i)] = h->dia_hi0 + i;
+    FVB_TRY(dalloc(h, &h->halo_glob, h->n_halo));
+    FVB_CUDA(memcpy_sync(st, h->halo_glob, h->halo_host.data(), sizeof(int64_t) * (size_t)h->n_halo, cudaMemcpyHostToDevice));
+  }
+  h->box = true;
+  h->dia_on = true;
+  FVB_TRY(box_fill(h));
+  if (h->scale_request != 1) {  // room for the Jacobi-scaled copy, taken at the same place of every assembly
+    bool ok = dalloc(h, &h->sinv, n) == FVB_OK;
+    for (int k = 0; k < 3 && ok; ++k) ok = dalloc(h, &h->dia_S[k], n + o[k]) == FVB_OK;
+    if (!ok) {
+      for (auto &u : h->dia_S) dfree(h, u);
+      dfree(h, h->sinv);
+    }
+  }
+  return FVB_OK;
+}
+
+// Does the face list of this handle's problem equal regulargrid's for the owned planes?  Reads a few faces to infer
+// (n2*n3, n3), compares the whole list and the node->row shifts on the device.  `dnodes_sorted`: Dirichlet table
+// of the whole problem (slab ranks only; empty for an unpartitioned problem, where no plane lies outside).
+int box_detect(fvb_handle h, const int64_t *d_nb, const std::vector<int64_t> &dnodes_sorted, BoxDesc *out, bool *ok) {
+  *ok = false;
+  cudaStream_t st = h->stream;
+  const int64_t N = h->n_nodes, lo = h->node_lo, hi = h->node_hi, F = h->n_faces;
+  if (F < 3 || hi - lo < 8 || h->nf_local < 2) return FVB_OK;
+  int64_t p0[2];
+  FVB_CUDA(memcpy_sync(st, p0, d_nb, sizeof(p0), cudaMemcpyDeviceToHost));
+  const int64_t plane = p0[1] - p0[0];
+  if (plane < 4 || N % plane || lo % plane || hi % plane || N / plane < 2) return FVB_OK;
+  GridDesc G = {};
+  G.n1 = N / plane;
+  G.p_lo = lo / plane + 1;
+  G.p_hi = hi / plane;
+  G.e_lo = G.p_lo > 1 ? G.p_lo - 1 : G.p_lo;
+  const bool halo = G.e_lo < G.p_lo;
+  if (p0[0] != (halo ? lo - plane + 1 : 1)) return FVB_OK;
+  const int64_t idx0 = halo ? plane : 0;
+  if (idx0 + 3 > F) return FVB_OK;
+  int64_t f[6];
+  FVB_CUDA(memcpy_sync(st, f, d_nb + 2 * idx0, sizeof(f), cudaMemcpyDeviceToHost));
+  const int64_t lin = lo + 1;
+  int k = 0;
+  if (G.p_lo < G.n1) {
+    if (f[0] != lin || f[1] != lin + plane) return FVB_OK;
+    k = 1;
+  }
+  if (f[2 * k] != lin || f[2 * k + 2] != lin || f[2 * k + 3] != lin + 1) return FVB_OK;
+  const int64_t n3 = f[2 * k + 1] - lin;
+  if (n3 < 2 || n3 >= plane || plane % n3 || plane / n3 < 2) return FVB_OK;
+  G.n3 = n3;
+  G.n2 = plane / n3;
+  if (box_face_count(G) != F) return FVB_OK;
+  BoxDesc B = {};
+  B.G = G;
+  B.n_own = hi - lo;
+  B.nd_owned = (hi - lo) - h->nf_local;
+  B.lo_kind = B.hi_kind = 0;
+  if (G.p_lo > 1) {
+    B.lo_kind = box_plane_kind(dnodes_sorted, lo - plane, plane);
+    if (B.lo_kind < 0 || (B.lo_kind == 1 && box_plane_kind(dnodes_sorted, lo, plane) != 1)) return FVB_OK;
+  }
+  if (G.p_hi < G.n1) {
+    B.hi_kind = box_plane_kind(dnodes_sorted, hi, plane);
+    if (B.hi_kind < 0 || (B.hi_kind == 1 && box_plane_kind(dnodes_sorted, hi - plane, plane) != 1)) return FVB_OK;
+  }
+  int *d_flag = nullptr;
+  FVB_TRY(dalloc(h, &d_flag, 2));
+  FVB_CUDA(cudaMemsetAsync(d_flag, 0, 2 * sizeof(int), st));
+  const int64_t nodes = (G.p_hi - G.e_lo + 1) * plane;
+  k_box_check<<<std::max(1, std::min(cdiv(nodes, kBlock), h->num_sms * 16)), kBlock, 0, st>>>(
+      B, reinterpret_cast<const longlong2 *>(d_nb), h->nodemap, d_flag);
+  h->tm.kernel_launches++;
+  int flag[2] = {1, 1};
+  cudaError_t e = memcpy_sync(st, flag, d_flag, sizeof(flag), cudaMemcpyDeviceToHost);
+  dfree(h, d_flag);
+  if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, std::string("box check: ") + cudaGetErrorString(e));
+  if (flag[0] || flag[1]) return FVB_OK;
+  *out = B;
+  *ok = true;
+  return FVB_OK;
+}
+
+// CSR arrays of a box problem, built on first demand (fvb_get_csr, forced CSR format).
+int ensure_csr(fvb_handle h) {
+  if (h->rowptr || !h->box) return FVB_OK;
+  cudaStream_t st = h->stream;
+  const int n = (int)h->nf_local;
+  if (h->nnz >= INT_MAX - 1)
+    return set_error(FVB_ERR_BAD_INPUT, "the CSR image of this rank's rows exceeds 32-bit local indices (" +
+                                            std::to_string(h->nnz) + " entries); use more ranks to fetch A");
+  int *d_cnt = nullptr, *d_scratch = nullptr;
+  FVB_TRY(dalloc(h, &d_cnt, (int64_t)n + 2));
+  FVB_TRY(dalloc(h, &d_scratch, scan_scratch_ints((int64_t)n + 1)));
+  int st_code = FVB_OK;
+  do {
+    if ((st_code = dalloc(h, &h->rowptr, (int64_t)n + 1 + kRowptrPad)) != FVB_OK) break;
+    if (n) k_box_csr_count<<<grid_for(n), kBlock, 0, st>>>(n, h->boxmask, d_cnt);
+    exclusive_scan(d_cnt, n, h->rowptr, d_scratch, st, &h->tm.kernel_launches);
+    k_fill_tail<<<1, kBlock, 0, st>>>(h->rowptr, n, kRowptrPad);
+    if ((st_code = dalloc(h, &h->colidx, h->nnz + kCsrPad)) != FVB_OK) break;
+    if ((st_code = dalloc(h, &h->vals, h->nnz + kCsrPad)) != FVB_OK) break;
+    cudaMemsetAsync(h->colidx + h->nnz, 0, sizeof(int) * kCsrPad, st);
+    cudaMemsetAsync(h->vals + h->nnz, 0, sizeof(double) * kCsrPad, st);
+    if (n) k_box_csr_fill<<<grid_for(n), kBlock, 0, st>>>(n, h->boxmask, h->rowptr, h->dia_off[1], h->dia_off[2], h->dia_nlo,
+                                                         h->dia_U[0], h->dia_U[1], h->dia_U[2], h->diag, h->colidx, h->vals);
+    h->tm.kernel_launches += 3;
+  } while (0);
+  cudaError_t e = cudaStreamSynchronize(st);
+  dfree(h, d_cnt); dfree(h, d_scratch);
+  if (st_code != FVB_OK) { dfree(h, h->rowptr); dfree(h, h->colidx); dfree(h, h->vals); return st_code; }
+  if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, std::string("lazy CSR build: ") + cudaGetErrorString(e));
   return FVB_OK;
 }
 
@@ -727,6 +928,7 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
     k_pcg_init<true><<<vg, kBlock, 0, st>>>(n, rhs, nullptr, 0, h->sinv, h->x, h->r, h->partials, h->ticket,
                                             h->scal, fin, pr);
   } else {
+    if (!h->dinv) FVB_TRY(dalloc(h, &h->dinv, n));
     k_make_dinv<<<vg, kBlock, 0, st>>>(n, h->diag, h->Dvec, sigma, h->dinv);
     h->tm.kernel_launches++;
     if (have_x0) {
@@ -807,6 +1009,7 @@ int pcg_mg_run(fvb_handle h, const double *rhs, bool have_x0, double rtol, int64
   h->last_solve_scaled = false;
   h->prof_seen = 0;
   h->prof_count = 0;
+  if (!h->dinv) FVB_TRY(dalloc(h, &h->dinv, n));
   k_set_scal<<<1, 1, 0, st>>>(h->scal, rtol, (long long)maxiter, (long long)h->hist_cap);
   k_make_dinv<<<vg, kBlock, 0, st>>>(n, h->diag, nullptr, 0.0, h->dinv);
   h->tm.kernel_launches += 2;
@@ -913,6 +1116,7 @@ int fvb_create(int device, fvb_handle *out) {
     if (!env || atoi(env) != 0) h->arena = new Arena(arena_chunk_alloc, arena_chunk_free);
   }
   if (const char *env = getenv("FVB_PCG_SCALING")) h->scale_request = atoi(env) == 0 ? 1 : 0;  // A/B measurements
+  if (const char *env = getenv("FVB_BOX")) h->box_request = atoi(env) == 0 ? 1 : 0;  // A/B: general path only
   if (const char *env = getenv("FVB_SPMV_FORMAT")) {  // initial fvb_set_spmv_format value
     const int f = atoi(env);
     if (f >= 0 && f <= 3) h->fmt_request = f;
@@ -1010,7 +1214,13 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
   if ((n_faces && (!neighbors || !aol || !cond)) || (n_nodes && !sources) || (nd && (!dnodes || !dheads)))
     return set_error(FVB_ERR_BAD_INPUT, "null input array");
   const int64_t n_own = node_hi1 - node_lo1 + 1;
-  if (n_own >= INT_MAX - 1 || 2 * n_faces >= INT_MAX - 1 || nd >= INT_MAX - 1)
+  // Local row / node indices are 32-bit.  The face-indexed arrays of the general path (adjacency, CSR) are too, but
+  // regulargrid-ordered problems never build them (box.cuh), so that limit is only enforced once the closed-form
+  // path has been ruled out, below.
+  if (n_own >= INT_MAX - 1 || nd >= INT_MAX - 1)
+    return set_error(FVB_ERR_BAD_INPUT, "per-GPU part too large for 32-bit local indices; use more ranks");
+  const bool faces_fit_32 = 2 * n_faces < INT_MAX - 1;
+  if (!faces_fit_32 && (h->box_request == 1 || h->fmt_request == 1 || n_faces > 4 * n_own))
     return set_error(FVB_ERR_BAD_INPUT, "per-GPU part too large for 32-bit local indices; use more ranks");
   const bool dbg = getenv("FVB_DEBUG") != nullptr;
   auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1031,27 +1241,42 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
   FVB_CUDA(cudaEventRecord(h->ev[0], st));
   int64_t *d_nb = nullptr, *d_dnodes = nullptr;
   double *d_cond = nullptr;
+  // inputs that already live on this device are read in place for the duration of the call (the neighbor list of
+  // a 512^3 slab is 6.4 GB: no second copy); everything retained beyond the call is copied as before
+  auto on_this_device = [&](const void *p) {
+    cudaPointerAttributes a;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice && a.device == h->device;
+  };
+  const bool nb_borrowed = n_faces > 0 && on_this_device(neighbors);
+  const bool cond_borrowed = n_cond > 0 && on_this_device(cond);
+  std::vector<int64_t> dn_sorted;  // ascending distinct 0-based Dirichlet nodes of the whole problem (slab ranks)
   int *d_dslot = nullptr, *d_cnt = nullptr, *d_scratch = nullptr, *d_err = nullptr;
   int64_t *d_dsorted = nullptr, *d_refs = nullptr;
   int *d_dsorted_slot = nullptr;
   unsigned long long *d_noff = nullptr;
   auto cleanup = [&]() {
-    dfree(h, d_nb); dfree(h, d_dnodes); dfree(h, d_cond); dfree(h, d_dslot); dfree(h, d_cnt); dfree(h, d_scratch); dfree(h, d_err);
+    if (!nb_borrowed) dfree(h, d_nb);
+    if (!cond_borrowed) dfree(h, d_cond);
+    d_nb = nullptr; d_cond = nullptr;
+    dfree(h, d_dnodes); dfree(h, d_dslot); dfree(h, d_cnt); dfree(h, d_scratch); dfree(h, d_err);
     dfree(h, d_dsorted); dfree(h, d_dsorted_slot); dfree(h, d_refs); dfree(h, d_noff);
   };
 #define A_TRY(expr) do { int s__ = (expr); if (s__ != FVB_OK) { cleanup(); free_problem(h); return s__; } } while (0)
 #define A_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); free_problem(h); \
     return set_error(FVB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
 
-  A_TRY(dalloc(h, &d_nb, 2 * n_faces));
+  if (nb_borrowed) d_nb = const_cast<int64_t *>(neighbors);
+  else A_TRY(dalloc(h, &d_nb, 2 * n_faces));
   A_TRY(dalloc(h, &h->aol, n_faces));
-  A_TRY(dalloc(h, &d_cond, n_cond));
+  if (cond_borrowed) d_cond = const_cast<double *>(cond);
+  else A_TRY(dalloc(h, &d_cond, n_cond));
   A_TRY(dalloc(h, &h->sources, n_own));
   A_TRY(dalloc(h, &d_dnodes, nd));
   A_TRY(dalloc(h, &h->dheads, nd));
-  A_CUDA(cudaMemcpyAsync(d_nb, neighbors, sizeof(int64_t) * 2 * (size_t)n_faces, cudaMemcpyDefault, st));
+  if (!nb_borrowed) A_CUDA(cudaMemcpyAsync(d_nb, neighbors, sizeof(int64_t) * 2 * (size_t)n_faces, cudaMemcpyDefault, st));
   A_CUDA(cudaMemcpyAsync(h->aol, aol, sizeof(double) * (size_t)n_faces, cudaMemcpyDefault, st));
-  A_CUDA(cudaMemcpyAsync(d_cond, cond, sizeof(double) * (size_t)n_cond, cudaMemcpyDefault, st));
+  if (!cond_borrowed) A_CUDA(cudaMemcpyAsync(d_cond, cond, sizeof(double) * (size_t)n_cond, cudaMemcpyDefault, st));
   A_CUDA(cudaMemcpyAsync(h->sources, sources, sizeof(double) * (size_t)n_own, cudaMemcpyDefault, st));
   A_CUDA(cudaMemcpyAsync(d_dnodes, dnodes, sizeof(int64_t) * (size_t)nd, cudaMemcpyDefault, st));
   A_CUDA(cudaMemcpyAsync(h->dheads, dheads, sizeof(double) * (size_t)nd, cudaMemcpyDefault, st));
@@ -1073,6 +1298,7 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
     std::vector<int> slot;
     dirichlet_table(hd, nodes, slot);  // sorted by node, last duplicate wins (host_util.h)
     nd_sorted = (int64_t)nodes.size();
+    dn_sorted = nodes;
     A_TRY(dalloc(h, &d_dsorted, nd_sorted));
     A_TRY(dalloc(h, &d_dsorted_slot, nd_sorted));
     A_CUDA(cudaMemcpyAsync(d_dsorted, nodes.data(), sizeof(int64_t) * nodes.size(), cudaMemcpyHostToDevice, st));
@@ -1124,6 +1350,53 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
     k_face_conductance<<<grid_for(n_faces), kBlock, 0, st>>>(n_faces, d_cond, n_cond, h->meta, h->aol, logk,
                                                              h->cface, d_err);
     h->tm.kernel_launches++;
+  }
+
+  // ---- closed-form path for regulargrid-ordered face lists (box.cuh): no adjacency, no CSR --------------------
+  if (h->box_request != 1 && h->fmt_request != 1 && nf_local >= 2) {
+    BoxDesc B;
+    bool is_box = false;
+    A_TRY(box_detect(h, d_nb, dn_sorted, &B, &is_box));
+    lap("box detection (sync)");
+    if (is_box) {
+      h->d_dsorted = d_dsorted; h->d_dsorted_slot = d_dsorted_slot; h->nd_sorted = nd_sorted;  // retained
+      d_dsorted = nullptr; d_dsorted_slot = nullptr;
+      A_TRY(box_install(h, B));
+      if (h->precond_request == 1) A_TRY(mg_setup(h, true));
+      A_CUDA(cudaEventRecord(h->ev[2], st));
+      int herr[ERR_COUNT];
+      A_CUDA(cudaMemcpyAsync(herr, d_err, sizeof(herr), cudaMemcpyDeviceToHost, st));
+      A_CUDA(cudaStreamSynchronize(st));
+      A_CUDA(cudaGetLastError());
+      if (herr[ERR_SRC_ON_DIRICHLET] != INT_MAX) {
+        int64_t node = 0;
+        memcpy_sync(h->stream, &node, d_dnodes + herr[ERR_SRC_ON_DIRICHLET], sizeof(int64_t), cudaMemcpyDeviceToHost);
+        cleanup(); free_problem(h);
+        return set_error(FVB_ERR_BAD_INPUT, "There cannot be a source at a Dirichlet node, but node " + std::to_string(node) +
+                                                " is a Dirichlet node where a source is located.");
+      }
+      if (herr[ERR_BAD_NODE] != INT_MAX) {
+        cleanup(); free_problem(h);
+        return set_error(FVB_ERR_BAD_INPUT, "node index out of range 1..N (neighbors or dirichletnodes entry " +
+                                                std::to_string(herr[ERR_BAD_NODE] + 1) + ")");
+      }
+      if (herr[ERR_BAD_META] != INT_MAX) {
+        cleanup(); free_problem(h);
+        return set_error(FVB_ERR_BAD_INPUT, "metaindex(" + std::to_string(herr[ERR_BAD_META] + 1) + ") is outside conductivities");
+      }
+      float msb = 0;
+      cudaEventElapsedTime(&msb, h->ev[0], h->ev[1]); h->tm.h2d_ms = msb;
+      cudaEventElapsedTime(&msb, h->ev[1], h->ev[2]); h->tm.assemble_ms = msb;
+      lap("box rows (sync)");
+      cleanup();
+      h->assembled = true;
+      h->halo_ready = (h->nranks == 1);
+      return FVB_OK;
+    }
+  }
+  if (!faces_fit_32) {
+    cleanup(); free_problem(h);
+    return set_error(FVB_ERR_BAD_INPUT, "per-GPU part too large for 32-bit local indices; use more ranks");
   }
 
   // ---- 3. adjacency ------------------------------------------------------------------------------
@@ -1237,6 +1510,26 @@ int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk
   FVB_TRY(check_handle(h, true));
   if (!cond) return set_error(FVB_ERR_BAD_INPUT, "null conductivities");
   cudaStream_t st = h->stream;
+  if (h->box_implicit) {
+    // grid-implicit problem (fvb_assemble_regulargrid): `cond` are the node values of the same planes as before
+    if (n_cond != h->nodek_n)
+      return set_error(FVB_ERR_BAD_INPUT, "grid-implicit problem: pass the node conductivities of the same " +
+                                              std::to_string(h->nodek_n) + " nodes as at assembly");
+    if (sources && !h->sources) FVB_TRY(dalloc(h, &h->sources, h->n_own_nodes));
+    FVB_CUDA(cudaMemcpyAsync(h->nodek, cond, sizeof(double) * (size_t)n_cond, cudaMemcpyDefault, st));
+    if (sources) FVB_CUDA(cudaMemcpyAsync(h->sources, sources, sizeof(double) * (size_t)h->n_own_nodes, cudaMemcpyDefault, st));
+    if (dheads) FVB_CUDA(cudaMemcpyAsync(h->dheads, dheads, sizeof(double) * (size_t)h->n_dirichlet, cudaMemcpyDefault, st));
+    FVB_CUDA(cudaEventRecord(h->ev[1], st));
+    h->logk = logk ? 1 : 0;
+    FVB_TRY(box_fill(h));
+    dfree(h, h->rowptr); dfree(h, h->colidx); dfree(h, h->vals);
+    if (h->mg && h->mg->ready) FVB_TRY(mg_setup(h, false));
+    FVB_CUDA(cudaEventRecord(h->ev[2], st));
+    FVB_CUDA(cudaStreamSynchronize(st));
+    float msi = 0;
+    cudaEventElapsedTime(&msi, h->ev[1], h->ev[2]); h->tm.assemble_ms = msi;
+    return FVB_OK;
+  }
   double *d_cond = nullptr;
   int *d_err = nullptr;
   FVB_TRY(dalloc(h, &d_cond, n_cond));
@@ -1262,7 +1555,7 @@ int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk
     h->tm.kernel_launches++;
   }
   ColKey key{(int)h->nf_local, h->row_start, h->halo_glob};
-  if (h->nf_local) {
+  if (h->nf_local && !h->box) {
     k_row_values<<<grid_for(h->nf_local), kBlock, 0, st>>>((int)h->nf_local, h->adjptr, h->adj_face, h->adj_col, key,
                                                            h->cface, h->sources, h->dheads, h->row2node, h->rowptr,
                                                            h->colidx, h->vals, h->diag, h->b, 0);
@@ -1270,7 +1563,10 @@ int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk
   }
   h->logk = logk ? 1 : 0;  // the gradient gather picks dc = c (log K) or aol (plain K) from this
   int st_dia = FVB_OK, st_mg = FVB_OK;
-  if (h->dia_on) st_dia = build_dia(h, false);
+  if (h->box) {
+    st_dia = box_fill(h);
+    dfree(h, h->rowptr); dfree(h, h->colidx); dfree(h, h->vals);  // a CSR image built on demand is stale now
+  } else if (h->dia_on) st_dia = build_dia(h, false);
   if (st_dia == FVB_OK && h->mg && h->mg->ready) st_mg = mg_setup(h, false);
   cudaEventRecord(h->ev[2], st);
   int herr[ERR_COUNT];
@@ -1287,6 +1583,157 @@ int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk
   return FVB_OK;
 }
 
+int fvb_assemble_regulargrid(fvb_handle h, const double mins[3], const double maxs[3], const int64_t ns[3],
+                             int64_t plane_lo, int64_t plane_hi, const double *nodehycos, int logmean, int logk,
+                             const double *sources, int64_t nd, const int64_t *dnodes, const double *dheads) {
+  FVB_TRY(check_handle(h, false));
+  if (!mins || !maxs || !ns || !nodehycos) return set_error(FVB_ERR_BAD_INPUT, "null grid description");
+  if (ns[0] < 2 || ns[1] < 2 || ns[2] < 2) return set_error(FVB_ERR_BAD_INPUT, "regulargrid needs at least 2 points per axis");
+  if (plane_lo < 1 || plane_hi > ns[0] || plane_hi < plane_lo) return set_error(FVB_ERR_BAD_INPUT, "bad plane range");
+  if (nd < 0 || (nd && (!dnodes || !dheads))) return set_error(FVB_ERR_BAD_INPUT, "bad Dirichlet arguments");
+  const int64_t plane = ns[1] * ns[2], n_nodes = ns[0] * plane;
+  const int64_t n_own = (plane_hi - plane_lo + 1) * plane;
+  if (n_own >= INT_MAX - 1 || nd >= INT_MAX - 1)
+    return set_error(FVB_ERR_BAD_INPUT, "per-GPU part too large for 32-bit local indices; use more ranks");
+  free_problem(h);
+  cudaStream_t st = h->stream;
+  h->n_nodes = n_nodes; h->node_lo = (plane_lo - 1) * plane; h->node_hi = plane_hi * plane; h->n_own_nodes = n_own;
+  h->n_faces = 0; h->n_dirichlet = nd; h->logk = logk ? 1 : 0; h->box_logmean = logmean ? 1 : 0;
+  const bool whole = plane_lo == 1 && plane_hi == ns[0];
+  BoxDesc B = {};
+  GridDesc &G = B.G;
+  G.n1 = ns[0]; G.n2 = ns[1]; G.n3 = ns[2];
+  auto axis = [](double lo, double hi, int64_t n) { double step = (hi - lo) / (double)(n - 1); return (lo + 1 * step) - lo; };
+  G.dx = axis(mins[0], maxs[0], ns[0]); G.dy = axis(mins[1], maxs[1], ns[1]); G.dz = axis(mins[2], maxs[2], ns[2]);
+  G.p_lo = plane_lo; G.p_hi = plane_hi; G.e_lo = plane_lo > 1 ? plane_lo - 1 : plane_lo;
+  const int64_t k_lo_plane = std::max<int64_t>(1, plane_lo - 1), k_hi_plane = std::min<int64_t>(ns[0], plane_hi + 1);
+  h->nodek_n = (k_hi_plane - k_lo_plane + 1) * plane;
+  h->nodek_ofs = (plane_lo - k_lo_plane) * plane;
+
+  int64_t *d_dnodes = nullptr;
+  int *d_dslot = nullptr, *d_cnt = nullptr, *d_scratch = nullptr, *d_err = nullptr, *d_flag = nullptr;
+  auto cleanup = [&]() { dfree(h, d_dnodes); dfree(h, d_dslot); dfree(h, d_cnt); dfree(h, d_scratch); dfree(h, d_err); dfree(h, d_flag); };
+#define G_TRY(expr) do { int s__ = (expr); if (s__ != FVB_OK) { cleanup(); free_problem(h); return s__; } } while (0)
+#define G_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); free_problem(h); \
+    return set_error(FVB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+  G_CUDA(cudaEventRecord(h->ev[0], st));
+  G_TRY(dalloc(h, &h->nodek, h->nodek_n));
+  G_TRY(dalloc(h, &d_dnodes, nd));
+  G_TRY(dalloc(h, &h->dheads, nd));
+  G_CUDA(cudaMemcpyAsync(h->nodek, nodehycos, sizeof(double) * (size_t)h->nodek_n, cudaMemcpyDefault, st));
+  if (sources) {
+    G_TRY(dalloc(h, &h->sources, n_own));
+    G_CUDA(cudaMemcpyAsync(h->sources, sources, sizeof(double) * (size_t)n_own, cudaMemcpyDefault, st));
+  }
+  if (nd) {
+    G_CUDA(cudaMemcpyAsync(d_dnodes, dnodes, sizeof(int64_t) * (size_t)nd, cudaMemcpyDefault, st));
+    G_CUDA(cudaMemcpyAsync(h->dheads, dheads, sizeof(double) * (size_t)nd, cudaMemcpyDefault, st));
+  }
+  G_CUDA(cudaEventRecord(h->ev[1], st));
+  // Dirichlet table of the whole problem: row offsets of a slab and the kind of the planes outside it
+  std::vector<int64_t> nodes;
+  h->row_start = 0;
+  if (!whole) {
+    std::vector<int64_t> hd((size_t)nd);
+    std::vector<int> slot;
+    if (nd) G_CUDA(memcpy_sync(st, hd.data(), d_dnodes, sizeof(int64_t) * (size_t)nd, cudaMemcpyDeviceToHost));
+    dirichlet_table(hd, nodes, slot);
+    h->nd_sorted = (int64_t)nodes.size();
+    G_TRY(dalloc(h, &h->d_dsorted, h->nd_sorted));
+    G_TRY(dalloc(h, &h->d_dsorted_slot, h->nd_sorted));
+    G_CUDA(memcpy_sync(st, h->d_dsorted, nodes.data(), sizeof(int64_t) * nodes.size(), cudaMemcpyHostToDevice));
+    G_CUDA(memcpy_sync(st, h->d_dsorted_slot, slot.data(), sizeof(int) * slot.size(), cudaMemcpyHostToDevice));
+    const int64_t below = std::lower_bound(nodes.begin(), nodes.end(), h->node_lo) - nodes.begin();
+    const int64_t valid = std::lower_bound(nodes.begin(), nodes.end(), n_nodes) - std::lower_bound(nodes.begin(), nodes.end(), (int64_t)0);
+    h->row_start = h->node_lo - below;
+    h->nf_global = n_nodes - valid;
+  }
+  // node map (getfreenodes / getnodei2dirichleti, src/FiniteVolume.jl:20-44), as in fvb_assemble
+  G_TRY(dalloc(h, &d_err, ERR_COUNT));
+  {
+    int init[ERR_COUNT];
+    for (int &v : init) v = INT_MAX;
+    G_CUDA(cudaMemcpyAsync(d_err, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  }
+  G_TRY(dalloc(h, &d_dslot, n_own));
+  G_TRY(dalloc(h, &d_cnt, n_own + 2));
+  G_TRY(dalloc(h, &d_scratch, scan_scratch_ints(n_own + 1)));
+  G_CUDA(cudaMemsetAsync(d_dslot, 0xFF, sizeof(int) * (size_t)n_own, st));
+  if (nd) {
+    k_mark_dirichlet<<<grid_for(nd), kBlock, 0, st>>>(d_dnodes, nd, n_nodes, h->node_lo, h->node_hi, h->sources, d_dslot, d_err);
+    h->tm.kernel_launches++;
+  }
+  int nf_local = 0;
+  k_free_flags<<<grid_for(n_own), kBlock, 0, st>>>(d_dslot, n_own, d_cnt);
+  h->tm.kernel_launches++;
+  exclusive_scan(d_cnt, n_own, d_cnt, d_scratch, st, &h->tm.kernel_launches);
+  G_CUDA(memcpy_sync(st, &nf_local, d_cnt + n_own, sizeof(int), cudaMemcpyDeviceToHost));
+  h->nf_local = nf_local;
+  if (whole) h->nf_global = nf_local;
+  G_TRY(dalloc(h, &h->nodemap, n_own));
+  G_TRY(dalloc(h, &h->row2node, nf_local));
+  k_finish_nodemap<<<grid_for(n_own), kBlock, 0, st>>>(d_dslot, d_cnt, n_own, h->nodemap, h->row2node);
+  h->tm.kernel_launches++;
+  dfree(h, d_dslot); dfree(h, d_cnt); dfree(h, d_scratch);
+  int herr[ERR_COUNT];
+  G_CUDA(memcpy_sync(st, herr, d_err, sizeof(herr), cudaMemcpyDeviceToHost));
+  if (herr[ERR_SRC_ON_DIRICHLET] != INT_MAX) {
+    int64_t node = 0;
+    memcpy_sync(st, &node, d_dnodes + herr[ERR_SRC_ON_DIRICHLET], sizeof(int64_t), cudaMemcpyDeviceToHost);
+    cleanup(); free_problem(h);
+    return set_error(FVB_ERR_BAD_INPUT, "There cannot be a source at a Dirichlet node, but node " + std::to_string(node) +
+                                            " is a Dirichlet node where a source is located.");
+  }
+  if (herr[ERR_BAD_NODE] != INT_MAX) {
+    cleanup(); free_problem(h);
+    return set_error(FVB_ERR_BAD_INPUT, "node index out of range 1..N (dirichletnodes entry " + std::to_string(herr[ERR_BAD_NODE] + 1) + ")");
+  }
+  // the diagonal format needs what box_detect checks for explicit lists
+  B.n_own = n_own;
+  B.nd_owned = n_own - nf_local;
+  const char *why = nullptr;
+  if (nf_local < 2) why = "fewer than two free nodes on this rank";
+  if (!why && plane_lo > 1) {
+    B.lo_kind = box_plane_kind(nodes, h->node_lo - plane, plane);
+    if (B.lo_kind < 0 || (B.lo_kind == 1 && box_plane_kind(nodes, h->node_lo, plane) != 1))
+      why = "the x-planes at the lower slab boundary mix free and Dirichlet nodes";
+  }
+  if (!why && plane_hi < ns[0]) {
+    B.hi_kind = box_plane_kind(nodes, h->node_hi, plane);
+    if (B.hi_kind < 0 || (B.hi_kind == 1 && box_plane_kind(nodes, h->node_hi - plane, plane) != 1))
+      why = "the x-planes at the upper slab boundary mix free and Dirichlet nodes";
+  }
+  if (!why) {
+    G_TRY(dalloc(h, &d_flag, 2));
+    G_CUDA(cudaMemsetAsync(d_flag, 0, 2 * sizeof(int), st));
+    k_box_check_shift<<<std::max(1, std::min(cdiv(n_own, kBlock), h->num_sms * 16)), kBlock, 0, st>>>(B, h->nodemap, d_flag);
+    h->tm.kernel_launches++;
+    int flag[2] = {0, 0};
+    G_CUDA(memcpy_sync(st, flag, d_flag, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag[1]) why = "the Dirichlet set does not leave the free nodes on the grid's diagonals";
+  }
+  if (why) {
+    cleanup(); free_problem(h);
+    return set_error(FVB_ERR_BAD_INPUT, std::string("fvb_assemble_regulargrid: ") + why +
+                                            " (build the face list with fvb_regulargrid and call fvb_assemble instead)");
+  }
+  h->box_implicit = true;
+  G_TRY(box_install(h, B));
+  if (h->precond_request == 1) G_TRY(mg_setup(h, true));
+  G_CUDA(cudaEventRecord(h->ev[2], st));
+  G_CUDA(cudaStreamSynchronize(st));
+  G_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->tm.h2d_ms = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->tm.assemble_ms = ms;
+  cleanup();
+#undef G_TRY
+#undef G_CUDA
+  h->assembled = true;
+  h->halo_ready = (h->nranks == 1);
+  return FVB_OK;
+}
+
 int fvb_sizes(fvb_handle h, int64_t *nf_local, int64_t *nnz_local, int64_t *row_start, int64_t *nf_global,
               int64_t *n_halo) {
   FVB_TRY(check_handle(h, true));
@@ -1300,6 +1747,7 @@ int fvb_sizes(fvb_handle h, int64_t *nf_local, int64_t *nnz_local, int64_t *row_
 
 int fvb_get_csr(fvb_handle h, int64_t *ptr, int64_t *idx, double *val) {
   FVB_TRY(check_handle(h, true));
+  FVB_TRY(ensure_csr(h));  // box problems keep no CSR image until somebody asks for A
   cudaStream_t st = h->stream;
   ColKey key{(int)h->nf_local, h->row_start, h->halo_glob};
   // export through a bounded device staging buffer (the int64 image of colidx can be 7 GiB)
@@ -1391,6 +1839,8 @@ int fvb_set_halo_plan(fvb_handle h, int n_peers, const int32_t *peer_ranks, cons
 
 int fvb_gradient_begin(fvb_handle h, const int64_t *neighbors) {
   FVB_TRY(check_handle(h, true));
+  if (h->box_implicit)
+    return set_error(FVB_ERR_STATE, "the gradient gather needs per-face arrays: assemble with fvb_assemble, not fvb_assemble_regulargrid");
   if (h->n_faces && !neighbors) return set_error(FVB_ERR_BAD_INPUT, "null neighbors");
   if (h->nranks != 1 || h->node_lo != 0 || h->node_hi != h->n_nodes)
     return set_error(FVB_ERR_STATE, "the gradient gather is implemented for unpartitioned problems");
@@ -1671,6 +2121,7 @@ int fvb_step(fvb_handle h, int rhs_slot, int u_slot, double dt, int out_slot, in
   cudaStream_t st = h->stream;
   const int vg = vgrid(h, n);
   const double sigma = 1.0 / dt;
+  if (!h->rhs) FVB_TRY(dalloc(h, &h->rhs, n));
   if (!adjoint) {
     k_axpby_D<<<vg, kBlock, 0, st>>>(n, h->slots[rhs_slot], h->slots[u_slot], h->Dvec, sigma, h->rhs);
     FVB_CUDA(cudaMemcpyAsync(h->x, h->slots[u_slot], sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
@@ -1745,6 +2196,19 @@ int fvb_get_spmv_format(fvb_handle h, int *active, int *n_offsets) {
   }
   if (active) *active = kind;
   if (n_offsets) *n_offsets = dia ? h->dia_K : 0;
+  return FVB_OK;
+}
+
+int fvb_set_assembly(fvb_handle h, int mode) {
+  FVB_TRY(check_handle(h, false));
+  if (mode != 0 && mode != 1) return set_error(FVB_ERR_BAD_INPUT, "assembly mode must be 0 (auto) or 1 (general path only)");
+  h->box_request = mode;
+  return FVB_OK;
+}
+
+int fvb_get_assembly(fvb_handle h, int *active) {
+  FVB_TRY(check_handle(h, true));
+  if (active) *active = h->box ? (h->box_implicit ? 2 : 1) : 0;
   return FVB_OK;
 }
 

@@ -94,6 +94,42 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo, int64_t node_hi
 int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk,
                       const double *sources, const double *dheads);
 
+/* ---- closed-form assembly of regulargrid-ordered problems ------------------------------------
+ * When the face list passed to fvb_assemble is exactly the one regulargrid emits for the owned
+ * x-planes (src/grid.jl:56-110: nodes z-fastest, each pushing its +x, +y, +z faces) and the
+ * Dirichlet set keeps the free nodes on the grid's three diagonals (e.g. the left/right planes of
+ * examples/box_model/ex.jl:27-37), the library verifies that on the device and then writes the
+ * rows straight into the symmetric-diagonal format: the faces of a node are known in closed form
+ * and already in ascending face order (-x,-y,-z,+x,+y,+z), which is the order assembleA/sparse!
+ * fold in (src/FiniteVolume.jl:94-107).  No adjacency and no CSR are built; fvb_get_csr produces
+ * the CSR image on demand, bit-identical to the general path's.  Face-indexed arrays of this path
+ * are addressed with 64-bit offsets, so only the NODE count of a rank must stay below 2^31.
+ *   mode: 0 = automatic (default), 1 = always the general path.  FVB_BOX=0 presets 1.
+ *   active: 0 = general path, 1 = closed form from the caller's arrays, 2 = grid-implicit. */
+int fvb_set_assembly(fvb_handle h, int mode);
+int fvb_get_assembly(fvb_handle h, int *active);
+
+/* Grid-implicit assembly: the problem that
+ *     coords, neighbors, aol, volumes = regulargrid(mins, maxs, ns)            (src/grid.jl:56)
+ *     k = nodehycos2neighborhycos(neighbors, nodehycos, logmean)               (src/grid.jl:14)
+ *     assembleA / assembleb(neighbors, aol, k, sources, dnodes, dheads, i->i, logk)
+ * describes, without any per-face array ever existing (1024^3 has 3.2e9 faces: 51 GB of neighbor
+ * pairs alone).  areasoverlengths come from the grid spacing exactly as regulargrid computes them,
+ * face conductivities from the two node values exactly as nodehycos2neighborhycos does; rows are
+ * bit-identical to fvb_regulargrid + fvb_nodehycos2neighborhycos + fvb_assemble.
+ *   plane_lo/hi  owned x-planes, 1-based inclusive (1, ns[0] on one GPU); owned nodes = those planes
+ *   nodehycos    node values, node order, of planes max(1,plane_lo-1) .. min(ns[0],plane_hi+1)
+ *   sources      owned nodes, or NULL for all zero
+ *   dnodes/heads the FULL Dirichlet lists
+ * Fails with FVB_ERR_BAD_INPUT when the Dirichlet set does not fit the diagonal format (then build
+ * the lists with fvb_regulargrid and use fvb_assemble).  fvb_update_values on such a problem takes
+ * the node values (same planes) as `cond`.  The adjoint gradient gather needs face arrays and is
+ * not available on it. */
+int fvb_assemble_regulargrid(fvb_handle h, const double mins[3], const double maxs[3], const int64_t ns[3],
+                             int64_t plane_lo, int64_t plane_hi, const double *nodehycos, int logmean, int logk,
+                             const double *sources, int64_t n_dirichlet, const int64_t *dnodes,
+                             const double *dheads);
+
 /* Sizes of this rank's part: free rows owned, stored entries, first owned row
  * (1-based global free index), global free count, halo columns referenced. */
 int fvb_sizes(fvb_handle h, int64_t *nf_local, int64_t *nnz_local, int64_t *row_start,
