@@ -9,7 +9,7 @@ registers it as module `fvb200`) rather than a plain import statement.
 """
 from . import _lib, jld
 from ._lib import FVBError, LIB_PATH
-from .api import (ConvergenceHistory, DEFAULT_MAXITER, DeviceArray, SQRT_EPS, SparseMatrixCSC, System, assembleA, assembleb,
+from .api import (ConvergenceHistory, DEFAULT_MAXITER, DeviceArray, MultiSystem, SQRT_EPS, SparseMatrixCSC, System, assembleA, assembleb,
                   freenodes2nodes, getfreenodes, solvediffusion)
 from .grid import grid_sizes, nodehycos2neighborhycos, regulargrid
 from .transient import (adaptivebackwardeulerstep, adjointintegrate, adjointintegrate_generic, backwardeulerintegrate,
@@ -17,7 +17,7 @@ from .transient import (adaptivebackwardeulerstep, adjointintegrate, adjointinte
                         getcontinuoussolution, gradientintegrate, integrate_g, integratedfdplambda)
 
 __all__ = [
-    "FVBError", "LIB_PATH", "DeviceArray", "ConvergenceHistory", "DEFAULT_MAXITER", "SQRT_EPS", "SparseMatrixCSC", "System",
+    "FVBError", "LIB_PATH", "DeviceArray", "ConvergenceHistory", "DEFAULT_MAXITER", "SQRT_EPS", "SparseMatrixCSC", "System", "MultiSystem",
     "assembleA", "assembleb", "freenodes2nodes", "getfreenodes", "solvediffusion", "grid_sizes",
     "nodehycos2neighborhycos", "regulargrid", "adaptivebackwardeulerstep", "adjointintegrate",
     "backwardeulerintegrate", "backwardeulerintegrate_generic", "adjointintegrate_generic", "gradientintegrate_generic", "fixedbackwardeulerstep", "getadjointfunctions",

@@ -24,6 +24,9 @@ SYMBOLS = [
     "fvb_step", "fvb_vec_to_nodes", "fvb_time_spmv", "fvb_device_alloc", "fvb_device_free", "fvb_device_copy", "fvb_regulargrid",
     "fvb_nodehycos2neighborhycos", "fvb_set_preconditioner", "fvb_get_preconditioner", "fvb_set_spmv_format", "fvb_get_spmv_format", "fvb_set_pcg_scaling", "fvb_get_pcg_scaling", "fvb_set_profiling", "fvb_get_timings", "fvb_sync",
     "fvb_set_assembly", "fvb_get_assembly", "fvb_assemble_regulargrid",
+    "fvb_solve_shifted", "fvb_multi_create", "fvb_multi_destroy", "fvb_multi_set_preconditioner", "fvb_multi_assemble",
+    "fvb_multi_assemble_regulargrid", "fvb_multi_sizes", "fvb_multi_solve", "fvb_multi_get_csr", "fvb_multi_get_b",
+    "fvb_multi_get_freenode", "fvb_multi_device_handle",
 ]
 
 

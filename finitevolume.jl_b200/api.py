@@ -360,6 +360,14 @@ class System:
                              C.byref(conv)))
         return int(iters.value), bool(conv.value)
 
+    def solve_shifted(self, rhs_slot, x0_slot, sigma, out_slot, rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER):
+        """(A + sigma D) x = rhs from x0, slot -> slot: the reference's linearsolver(A, rhs, x0) hook
+        (src/transient.jl:136) on the resident matrix."""
+        iters, conv = C.c_int64(), C.c_int()
+        check(lib().fvb_solve_shifted(self._h, C.c_int(rhs_slot), C.c_int(x0_slot), C.c_double(sigma), C.c_int(out_slot),
+                                      C.c_double(rtol), C.c_int64(int(maxiter)), C.byref(iters), C.byref(conv)))
+        return int(iters.value), bool(conv.value)
+
     # ---- adjoint gradient gather -------------------------------------------------------------------
     def gradient_begin(self, neighbors):
         nb_p, _, keep = _arg(neighbors, np.int64)
@@ -440,13 +448,127 @@ class System:
         check(lib().fvb_sync(self._h))
 
 
+class MultiSystem:
+    """One problem spread over several GPUs of the box from ONE process and one calling thread (an fvb_multi):
+    the whole-problem arrays go in exactly as into solvediffusion, the library partitions, connects the devices
+    over NVLink peer memory and solves; see include/fvb200.h "single-process multi-GPU front end"."""
+
+    def __init__(self, devices=None, ndev=None):
+        if devices is None:
+            if ndev is None:
+                n = C.c_int()
+                check(lib().fvb_device_count(C.byref(n)))
+                ndev = n.value
+            devices = list(range(int(ndev)))
+        self.devices = [int(d) for d in devices]
+        ids = (C.c_int * len(self.devices))(*self.devices)
+        self._m = C.c_void_p()
+        check(lib().fvb_multi_create(C.c_int(len(self.devices)), ids, C.byref(self._m)))
+        self.n_nodes = 0
+
+    def close(self):
+        if getattr(self, "_m", None) is not None and self._m:
+            lib().fvb_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_preconditioner(self, kind="jacobi", nu=0, omega=0.0, oc=0.0):
+        check(lib().fvb_multi_set_preconditioner(self._m, C.c_int({"jacobi": 0, "mg": 1}[kind]), C.c_int(int(nu)),
+                                                 C.c_double(omega), C.c_double(oc)))
+
+    def assemble(self, neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
+                 metaindex=None, logtransformconductivity=False):
+        nb = _pairs(neighbors)
+        F = nb.size // 2
+        aol, cond, src = f64(areasoverlengths).reshape(-1), f64(conductivities).reshape(-1), f64(sources).reshape(-1)
+        dn, dh = i64(dirichletnodes), f64(dirichletheads)
+        if aol.size != F:
+            raise ValueError("areasoverlengths and neighbors differ in length")
+        if dn.size != dh.size:
+            raise ValueError("dirichletnodes and dirichletheads differ in length")
+        meta = _metaindex_table(metaindex, F)
+        if meta is None and cond.size < F:
+            raise IndexError("conductivities is shorter than neighbors")
+        check(lib().fvb_multi_assemble(self._m, C.c_int64(src.size), C.c_int64(F), ptr(nb), ptr(aol), ptr(cond),
+                                       C.c_int64(cond.size), ptr(meta), C.c_int(int(bool(logtransformconductivity))),
+                                       ptr(src), C.c_int64(dn.size), ptr(dn), ptr(dh)))
+        self.n_nodes = src.size
+        return self
+
+    def assemble_regulargrid(self, mins, maxs, ns, nodehycos, sources, dirichletnodes, dirichletheads, logmean=True,
+                             logtransformconductivity=True):
+        mn, mx, nn = f64(mins), f64(maxs), i64(ns)
+        k = f64(nodehycos).reshape(-1)
+        src = None if sources is None else f64(sources).reshape(-1)
+        dn, dh = i64(dirichletnodes), f64(dirichletheads)
+        if k.size != int(np.prod(nn)):
+            raise ValueError("nodehycos must hold one value per node")
+        check(lib().fvb_multi_assemble_regulargrid(self._m, ptr(mn), ptr(mx), ptr(nn), ptr(k), C.c_int(int(bool(logmean))),
+                                                   C.c_int(int(bool(logtransformconductivity))), ptr(src),
+                                                   C.c_int64(dn.size), ptr(dn), ptr(dh)))
+        self.n_nodes = k.size
+        return self
+
+    def sizes(self):
+        nf, nnz, nd = C.c_int64(), C.c_int64(), C.c_int()
+        lo = (C.c_int64 * len(self.devices))()
+        hi = (C.c_int64 * len(self.devices))()
+        check(lib().fvb_multi_sizes(self._m, C.byref(nf), C.byref(nnz), C.byref(nd), lo, hi))
+        return dict(nf_global=nf.value, nnz_global=nnz.value, ndev=nd.value, node_ranges=list(zip(list(lo), list(hi))))
+
+    def device_system(self, i):
+        """A non-owning System view of device i's handle (formats, timings, assembly kind ...)."""
+        hnd = C.c_void_p()
+        check(lib().fvb_multi_device_handle(self._m, C.c_int(int(i)), C.byref(hnd)))
+        s = System.__new__(System)
+        s._h, s.device, s.nranks, s.rank = hnd, self.devices[i], len(self.devices), i
+        s.node_lo, s.node_hi = self.sizes()["node_ranges"][i]
+        s.close = lambda: None  # owned by the MultiSystem
+        return s
+
+    def solve(self, rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER, want_x=False, hist_cap=None):
+        sz = self.sizes()
+        head = np.empty(self.n_nodes, np.float64)
+        x = np.empty(sz["nf_global"], np.float64) if want_x else None
+        cap = int(min(maxiter, 1 << 24) if hist_cap is None else hist_cap)
+        hist = np.empty(max(cap, 1), np.float64)
+        iters, conv = C.c_int64(), C.c_int()
+        check(lib().fvb_multi_solve(self._m, C.c_double(rtol), C.c_int64(int(maxiter)), ptr(head), ptr(x), C.byref(iters),
+                                    C.byref(conv), ptr(hist), C.c_int64(cap)))
+        ch = ConvergenceHistory(bool(conv.value), int(iters.value), {"resnorm": hist[:min(iters.value, cap)].copy()})
+        return head, x, ch
+
+    def csr(self):
+        sz = self.sizes()
+        p = np.empty(sz["nf_global"] + 1, np.int64)
+        idx = np.empty(sz["nnz_global"], np.int64)
+        val = np.empty(sz["nnz_global"], np.float64)
+        check(lib().fvb_multi_get_csr(self._m, ptr(p), ptr(idx), ptr(val)))
+        return p, idx, val
+
+    def b(self):
+        out = np.empty(self.sizes()["nf_global"], np.float64)
+        check(lib().fvb_multi_get_b(self._m, ptr(out)))
+        return out
+
+    def freenode(self):
+        out = np.empty(self.n_nodes, np.uint8)
+        check(lib().fvb_multi_get_freenode(self._m, ptr(out)))
+        return out.astype(bool)
+
+
 class SparseMatrixCSC:
     """The `A` of the reference's return tuples: a SparseMatrixCSC{Float64,Int64} image whose
     arrays are fetched from the GPU on first access (A is symmetric, so the CSR arrays kept
     on the device are its CSC arrays; src/FiniteVolume.jl:107)."""
 
-    def __init__(self, system: System):
-        self._sys = system
+    def __init__(self, system):
+        self._sys = system  # a System or a MultiSystem
         s = system.sizes()
         self.m = self.n = s["nf_global"]
         self._arrays = None
@@ -528,7 +650,7 @@ def freenodes2nodes(result, sources, dirichletnodes, dirichletheads, device=0):
 
 def solvediffusion(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
                    maxiter=DEFAULT_MAXITER, rtol=SQRT_EPS, metaindex=None, logtransformconductivity=False, device=0,
-                   precond="jacobi"):
+                   precond="jacobi", devices=None):
     """src/FiniteVolume.jl:157-165 -> (head, ch, A, b, freenode).
 
     Differences from the reference, both mandated by north_star: the preconditioner is
@@ -536,7 +658,16 @@ def solvediffusion(neighbors, areasoverlengths, conductivities, sources, dirichl
     raised from 400 accordingly); `rtol` exposes IterativeSolvers' `tol` (same default).
     precond="mg" selects the aggregation-multigrid V-cycle (box-structured grids),
     "auto" uses it when the matrix qualifies and Jacobi otherwise."""
-    s = System(device)
+    if devices is not None and len(devices) > 1:
+        # one process, several GPUs (fvb_multi): same call, same return tuple
+        ms = MultiSystem(devices)
+        if precond in ("mg", "auto"):
+            ms.set_preconditioner("mg")
+        ms.assemble(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads, metaindex,
+                    logtransformconductivity)
+        head, _, ch = ms.solve(rtol=rtol, maxiter=maxiter)
+        return head, ch, SparseMatrixCSC(ms), ms.b(), ms.freenode()
+    s = System(device if devices is None else devices[0])
     if precond in ("mg", "auto"):
         s.set_preconditioner("mg")  # before assemble: silently stays on Jacobi when the matrix does not qualify
     s.assemble(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,

@@ -102,6 +102,8 @@ struct fvb_handle_s {
   fvb::Comm *comm = nullptr;
   std::vector<int> peers;
   std::vector<int64_t> send_counts, recv_counts;
+  std::vector<int64_t> send_first;  // per plan peer: first row of its send list when that list is a contiguous run
+  bool send_contig = false;         // every peer's send list is one ascending run (slab partitions: a plane)
   int32_t *send_rows = nullptr;
   double *sendbuf = nullptr;
   int64_t n_send = 0;

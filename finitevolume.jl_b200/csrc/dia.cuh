@@ -190,10 +190,12 @@ k_spmv_dia(int nrows, DiaDesc D, const double *__restrict__ x, double *__restric
   }
   if (DOT) {
     double s = block_sum(dot);
-    if (last_block_sum1(s, partials, ticket, &s)) {
-      const bool ok = finalize_mode != 2 || peer_allreduce_thread(pr, &s, 1, scal);
-      scal->red[0] = s;
-      if (ok && finalize_mode >= 1) scal->uc = s;
+    if (last_block_sum1_all(s, partials, ticket, &s) && threadIdx.x < 32) {
+      const bool ok = finalize_mode != 2 || peer_allreduce_warp(pr, &s, 1, scal);
+      if (threadIdx.x == 0) {
+        scal->red[0] = s;
+        if (ok && finalize_mode >= 1) scal->uc = s;
+      }
     }
   }
 }

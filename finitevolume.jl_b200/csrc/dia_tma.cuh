@@ -99,7 +99,30 @@ inline size_t dia_tma_smem_bytes(const DiaTmaLayout &L) { return (size_t)L.bar_o
 
 __device__ __forceinline__ void dia_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kDiaTmaRows) : "memory"); }
 
+// Tiles are dealt in the order "interior first, edge tiles last": the tiles at the two ends of the owned range
+// are the only ones that read halo values, so a multi-GPU product can start on its interior while the neighbours'
+// planes are still in flight and wait for them (FusedWait) only when it gets there.
+struct DiaTileOrder {
+  int first_int, n_int;  // interior tiles are first_int .. first_int + n_int - 1
+  __device__ __forceinline__ int operator()(int v) const {
+    if (v < n_int) return first_int + v;
+    const int e = v - n_int;
+    return e < first_int ? e : e + n_int;
+  }
+};
+__device__ __forceinline__ DiaTileOrder dia_tile_order(int nrows, int64_t reach) {
+  constexpr int T = kDiaTmaTile;
+  DiaTileOrder o;
+  const int64_t first = (reach + T - 1) / T;
+  const int64_t last = ((int64_t)nrows - T - reach) >= 0 ? ((int64_t)nrows - T - reach) / T : -1;
+  o.first_int = (int)first;
+  o.n_int = last >= first ? (int)(last - first + 1) : 0;
+  if (o.n_int == 0) o.first_int = 0;
+  return o;
+}
+
 // one row straight from global memory (edge tiles): identical arithmetic to k_spmv_dia
+// (halo columns through L2: their values may have arrived from the neighbour GPU while this kernel was running)
 template <int K, bool UNIT>
 __device__ __forceinline__ double dia_row_direct(const DiaDesc &D, const double *__restrict__ x, int64_t r, double xr) {
   double acc = 0.0;
@@ -108,7 +131,7 @@ __device__ __forceinline__ double dia_row_direct(const DiaDesc &D, const double 
     const double lo = __ldg(&D.U[k][r]);
     if (lo != 0.0) {
       const int64_t il = r - D.off[k];
-      const double xv = il >= 0 ? __ldg(&x[il]) : __ldg(&x[D.xindex(D.row_start + il)]);
+      const double xv = il >= 0 ? __ldg(&x[il]) : __ldcg(&x[D.xindex(D.row_start + il)]);
       acc = __dadd_rn(acc, __dmul_rn(lo, xv));
     }
   }
@@ -118,7 +141,7 @@ __device__ __forceinline__ double dia_row_direct(const DiaDesc &D, const double 
     const double up = __ldg(&D.U[k][D.off[k] + r]);
     if (up != 0.0) {
       const int64_t iu = r + D.off[k];
-      const double xv = iu < D.nf ? __ldg(&x[iu]) : __ldg(&x[D.xindex(D.row_start + iu)]);
+      const double xv = iu < D.nf ? __ldg(&x[iu]) : __ldcg(&x[D.xindex(D.row_start + iu)]);
       acc = __dadd_rn(acc, __dmul_rn(up, xv));
     }
   }
@@ -129,7 +152,7 @@ template <bool DOT, int K, bool UNIT>
 __global__ void __launch_bounds__(kDiaTmaThreads, kDiaTmaCtasPerSm)
 k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ x, double *__restrict__ y,
                const double *__restrict__ Dvec, double sigma, double *__restrict__ partials, unsigned int *ticket,
-               PcgScal *scal, int finalize_mode, PeerRed pr) {
+               PcgScal *scal, int finalize_mode, PeerRed pr, FusedWait fw) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (DOT && scal->done) return;
   constexpr int T = kDiaTmaTile;
@@ -141,6 +164,7 @@ k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ 
   int *const is_last = reinterpret_cast<int *>(wsum + kDiaTmaRows / 32);
   const int t = threadIdx.x;
   const int ntiles = (nrows + T - 1) / T;
+  const DiaTileOrder order = dia_tile_order(nrows, L.reach);
   if (t == 0) {
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&full[s], 1);
@@ -154,7 +178,8 @@ k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ 
     // ---------------- producer warp: one elected lane drives the TMA unit ----------------
     if (t == kDiaTmaRows) {
       int stage = 0, use = 0;  // use = how often this stage has been filled before
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int v = blockIdx.x; v < ntiles; v += gridDim.x) {
+        const int tile = order(v);
         if (use > 0) mbar_wait(&empty[stage], (uint32_t)((use - 1) & 1));
         const int cur = stage;
         if (++stage == nstages) { stage = 0; ++use; }
@@ -189,7 +214,9 @@ k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ 
   // ---------------- consumers: thread t owns rows r0 + t, r0 + kDiaTmaRows + t of every tile ----------------
   double dot = 0.0;
   int nxt = 0, use = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  bool halo_here = fw.n == 0;
+  for (int v = blockIdx.x; v < ntiles; v += gridDim.x) {
+    const int tile = order(v);
     const int stage = nxt;
     const uint32_t parity = (uint32_t)(use & 1);
     if (++nxt == nstages) { nxt = 0; ++use; }
@@ -224,6 +251,11 @@ k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ 
         acc[j] = a;
       }
     } else {
+      if (!halo_here) {  // first edge tile of this CTA: the neighbours' planes must have landed (CTA-uniform branch)
+        if (t < fw.n && !wait_flag(fw.flag[t], fw.seq)) { *fw.error = 1; scal->done = 1; scal->converged = 0; }
+        dia_consumer_sync();
+        halo_here = true;
+      }
 #pragma unroll
       for (int j = 0; j < kDiaTmaR; ++j) {
         const int64_t r = r0 + j * kDiaTmaRows + t;
@@ -270,12 +302,15 @@ k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ 
       dia_consumer_sync();
       if ((t & 31) == 0) wsum[t >> 5] = q;
       dia_consumer_sync();
-      if (t == 0) {
+      if (t < 32) {
         double tot = 0.0;
-        for (int w = 0; w < kDiaTmaRows / 32; ++w) tot += wsum[w];
-        const bool ok = finalize_mode != 2 || peer_allreduce_thread(pr, &tot, 1, scal);
-        scal->red[0] = tot;
-        if (ok && finalize_mode >= 1) scal->uc = tot;
+        if (t == 0)
+          for (int w = 0; w < kDiaTmaRows / 32; ++w) tot += wsum[w];
+        const bool ok = finalize_mode != 2 || peer_allreduce_warp(pr, &tot, 1, scal);
+        if (t == 0) {
+          scal->red[0] = tot;
+          if (ok && finalize_mode >= 1) scal->uc = tot;
+        }
       }
     }
   }

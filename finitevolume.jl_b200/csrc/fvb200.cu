@@ -147,7 +147,7 @@ void free_problem(fvb_handle h) {
   h->hist_cap = 0;
   h->assembled = false;
   h->halo_ready = false;
-  h->peers.clear(); h->send_counts.clear(); h->recv_counts.clear();
+  h->peers.clear(); h->send_counts.clear(); h->recv_counts.clear(); h->send_first.clear(); h->send_contig = false;
   h->halo_host.clear();
   h->n_send = 0;
 }
@@ -191,24 +191,35 @@ int ensure_hist(fvb_handle h, int64_t cap) {
 }
 
 // ---- multi-rank plumbing -----------------------------------------------------------------
-int halo_exchange(fvb_handle h, double *vec) {
+// pushed: the producer of `vec` already stored the boundary rows into the neighbours' halo slots under a freshly
+//         drawn sequence number (fused_push); defer: the consumer kernel waits for the neighbours' flags itself
+//         (dia_tma.cuh: FusedWait) -- filled here instead of launching k_halo_wait.
+int halo_exchange(fvb_handle h, double *vec, bool pushed = false, FusedWait *defer = nullptr) {
   if (h->nranks == 1) return FVB_OK;
   if (!h->halo_ready) return set_error(FVB_ERR_STATE, "fvb_set_halo_plan has not been called on this rank");
   if (h->peer && h->peer->active && vec == h->u) {
     // NVLink peer stores + flags (peer.cuh)
     PeerState &P = *h->peer;
-    const unsigned long long seq = ++P.halo_seq;
-    if (P.push.npeers > 0) {
+    const unsigned long long seq = pushed ? P.halo_seq : ++P.halo_seq;
+    if (!pushed && P.push.npeers > 0) {
       const int g = std::max(1, std::min(cdiv(h->n_send, kBlock), h->num_sms * 2));
       k_halo_push<<<g, kBlock, 0, h->stream>>>(P.tab, P.push, h->send_rows, vec, seq, h->ticket + 1);
       h->tm.kernel_launches++;
     }
     if (P.wait.npeers > 0) {
-      k_halo_wait<<<1, 32, 0, h->stream>>>(P.mail, P.wait, seq, h->scal);
-      h->tm.kernel_launches++;
+      if (defer && P.wait.npeers <= 2) {
+        defer->n = P.wait.npeers;
+        for (int k = 0; k < P.wait.npeers; ++k) defer->flag[k] = &P.mail->hseq[P.wait.peer[k]];
+        defer->seq = seq;
+        defer->error = &P.mail->error;
+      } else {
+        k_halo_wait<<<1, 32, 0, h->stream>>>(P.mail, P.wait, seq, h->scal);
+        h->tm.kernel_launches++;
+      }
     }
     return FVB_OK;
   }
+  if (pushed) return set_error(FVB_ERR_STATE, "internal: fused halo push without the peer-memory path");
   if (h->n_send > 0) {
     k_pack<<<grid_for(h->n_send), kBlock, 0, h->stream>>>(h->n_send, h->send_rows, vec, h->sendbuf);
     h->tm.kernel_launches++;
@@ -241,6 +252,29 @@ int red_mode(fvb_handle h, PeerRed *pr) {
   return 0;
 }
 
+// Descriptor for pushing the boundary rows of h->u from the kernel that writes them (pcg.cuh: k_update_u): possible
+// when the peer-memory path is up and every neighbour receives one contiguous run of rows (slab partitions).
+// Draws the halo sequence number; the product that follows must be launched with pushed = true.
+FusedPush fused_push(fvb_handle h) {
+  FusedPush fp = {};
+  if (h->nranks == 1 || !h->halo_ready || !(h->peer && h->peer->active) || !h->send_contig) return fp;
+  PeerState &P = *h->peer;
+  if (P.push.npeers < 1 || P.push.npeers > 2 || getenv("FVB_FUSED_HALO_OFF")) return fp;
+  int k = 0;
+  for (size_t p = 0; p < h->peers.size(); ++p) {
+    if (h->send_counts[p] <= 0) continue;
+    const int peer = h->peers[p];
+    fp.dst[k] = P.tab.u[peer] + P.push.dst_off[k];
+    fp.begin[k] = h->send_first[p];
+    fp.count[k] = h->send_counts[p];
+    fp.flag[k] = &P.tab.mail[peer]->hseq[h->rank];
+    ++k;
+  }
+  fp.npeers = k;
+  fp.seq = ++P.halo_seq;
+  return fp;
+}
+
 // Sum scal->red[0..count) over the ranks and advance the recurrence (mode: FIN_*).
 int allreduce_fin(fvb_handle h, int count, int mode) {
   if (h->nranks == 1) return FVB_OK;
@@ -265,7 +299,7 @@ int allreduce_fin(fvb_handle h, int count, int mode) {
 // once per instantiation and device (again only if a larger layout shows up).
 template <bool DOT, int K, bool UNIT>
 int launch_dia_tma(fvb_handle h, int n, const DiaDesc &D, const DiaTmaLayout &L, const double *vec, double *out,
-                   double sigma, int fin, PeerRed pr) {
+                   double sigma, int fin, PeerRed pr, FusedWait fw) {
   static int opted[64] = {};
   const int smem = (int)dia_tma_smem_bytes(L);
   const int dev = h->device & 63;
@@ -276,7 +310,7 @@ int launch_dia_tma(fvb_handle h, int n, const DiaDesc &D, const DiaTmaLayout &L,
   const int ntiles = cdiv(n, kDiaTmaTile);
   const int grid = std::max(1, std::min(ntiles, h->num_sms * kDiaTmaCtasPerSm));
   k_spmv_dia_tma<DOT, K, UNIT><<<grid, kDiaTmaThreads, smem, h->stream>>>(n, D, L, vec, out, h->Dvec, sigma, h->partials,
-                                                                        h->ticket, h->scal, fin, pr);
+                                                                        h->ticket, h->scal, fin, pr, fw);
   return FVB_OK;
 }
 
@@ -302,10 +336,25 @@ bool use_dia_tma(fvb_handle h, const double *vec, const DiaTmaLayout &L, bool sc
 // fuse: let the kernel finish u.Au across the ranks itself when the peer-memory path allows (the caller
 // must then skip allreduce_fin: *fin_out reports the finalize mode used).
 int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot, bool scaled = false, bool fuse = false,
-                int *fin_out = nullptr) {
+                int *fin_out = nullptr, bool pushed = false) {
   if (h->box && h->fmt_request == 1) FVB_TRY(ensure_csr(h));  // forced CSR on a problem assembled without one
-  FVB_TRY(halo_exchange(h, vec));
   const int n = (int)h->nf_local;
+  // which kernel serves this product decides how the halo arrives: the TMA diagonal pipeline waits for the
+  // neighbours' planes itself, right before its edge tiles; every other kernel gets a k_halo_wait launch
+  const bool use_dia = h->dia_on && h->fmt_request != 1 && n > 0;
+  DiaDesc D = {};
+  DiaTmaLayout L = {};
+  bool tma = false;
+  if (use_dia) {
+    D.K = h->dia_K;
+    for (int k = 0; k < kDiaMaxOff; ++k) { D.off[k] = h->dia_off[k]; D.U[k] = scaled ? h->dia_S[k] : h->dia_U[k]; }
+    D.diag = h->diag; D.row_start = h->row_start; D.nf = h->nf_local;
+    D.lo0 = h->dia_lo0; D.nlo = h->dia_nlo; D.hi0 = h->dia_hi0; D.nhi = h->dia_nhi;
+    L = dia_tma_layout(D.K, D.off, scaled);
+    tma = use_dia_tma(h, vec, L, scaled);
+  }
+  FusedWait fw = {};
+  FVB_TRY(halo_exchange(h, vec, pushed, (tma && !getenv("FVB_FUSED_HALO_OFF")) ? &fw : nullptr));
   PeerRed pr = {nullptr, 0ull};
   int fin = h->nranks == 1 ? 1 : 0;
   if (dot && fuse) fin = red_mode(h, &pr);
@@ -323,17 +372,10 @@ int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot, 
     sample = h->prof_count++;
     cudaEventRecord(h->prof_ev[2 * sample], h->stream);
   }
-  if (h->dia_on && h->fmt_request != 1) {
-    DiaDesc D;
-    D.K = h->dia_K;
-    for (int k = 0; k < kDiaMaxOff; ++k) { D.off[k] = h->dia_off[k]; D.U[k] = scaled ? h->dia_S[k] : h->dia_U[k]; }
-    D.diag = h->diag; D.row_start = h->row_start; D.nf = h->nf_local;
-    D.lo0 = h->dia_lo0; D.nlo = h->dia_nlo; D.hi0 = h->dia_hi0; D.nhi = h->dia_nhi;
+  if (use_dia) {
     const int dg = std::min(cdiv(n, kBlock * kDiaRowsPerThread), h->num_sms * kDiaCtasPerSm);
-    const DiaTmaLayout L = dia_tma_layout(D.K, D.off, scaled);
-    const bool tma = use_dia_tma(h, vec, L, scaled);
 #define FVB_DIA_LAUNCH(DOTV, KV, UV)                                                                                \
-  if (tma) FVB_TRY((launch_dia_tma<DOTV, KV, UV>(h, n, D, L, vec, out, sigma, fin, pr)));                             \
+  if (tma) FVB_TRY((launch_dia_tma<DOTV, KV, UV>(h, n, D, L, vec, out, sigma, fin, pr, fw)));                         \
   else k_spmv_dia<DOTV, KV, UV><<<dg, kBlock, 0, h->stream>>>(n, D, vec, out, h->Dvec, sigma, h->partials, h->ticket, \
                                                               h->scal, fin, pr)
 #define FVB_DIA_K(DOTV, UV)                                   \
@@ -950,10 +992,11 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
   while (!stop) {
     int64_t todo = std::min<int64_t>(batch, maxiter - enq);
     for (int64_t it = 0; it < todo; ++it) {
-      if (sc) k_update_u<true><<<vg, kBlock, 0, st>>>(n, nullptr, h->r, h->u, h->x, h->scal);
-      else k_update_u<false><<<vg, kBlock, 0, st>>>(n, h->dinv, h->r, h->u, h->x, h->scal);
+      const FusedPush fp = fused_push(h);  // slab ranks over peer memory: the halo push rides on k_update_u
+      if (sc) k_update_u<true><<<vg, kBlock, 0, st>>>(n, nullptr, h->r, h->u, h->x, h->scal, fp, h->ticket + 1);
+      else k_update_u<false><<<vg, kBlock, 0, st>>>(n, h->dinv, h->r, h->u, h->x, h->scal, fp, h->ticket + 1);
       h->tm.kernel_launches++;
-      FVB_TRY(launch_spmv(h, h->u, h->c, sigma, true, sc, true, &fin));
+      FVB_TRY(launch_spmv(h, h->u, h->c, sigma, true, sc, true, &fin, fp.npeers > 0));
       if (!fin) FVB_TRY(allreduce_fin(h, 1, FIN_UC));
       fin = red_mode(h, &pr);
       if (sc) k_update_xr<true><<<vg, kBlock, 0, st>>>(n, h->c, h->diag, h->r, h->partials, h->ticket, h->scal, h->hist, fin, pr);
@@ -971,7 +1014,7 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
     have_prev = true;
     slot ^= 1;
     if (enq >= maxiter) stop = true;
-    if (batch < 64) batch *= 2;
+    if (batch < 32) batch *= 2;
   }
   if (sc) k_finish_x_scaled<<<vg, kBlock, 0, st>>>(n, h->u, h->sinv, h->x, h->scal);
   else k_finish_x<<<vg, kBlock, 0, st>>>(n, h->u, h->x, h->scal);
@@ -1072,6 +1115,34 @@ int pcg_mg_run(fvb_handle h, const double *rhs, bool have_x0, double rtol, int64
     }
   }
   FVB_CUDA(cudaGetLastError());
+  return FVB_OK;
+}
+
+// Push/wait tables of the peer-memory halo exchange from the installed halo plan (P.tab already holds every
+// rank's vector and mailbox as seen from this process); shared by fvb_peer_import (CUDA IPC mappings) and the
+// single-process multi-device front end (multi_impl.h: plain peer access).
+int peer_finish_plan(fvb_handle h, const int64_t *send_dst_index) {
+  PeerState &P = *h->peer;
+  P.push = HaloPlanDev{};
+  P.wait = HaloPlanDev{};
+  long long so = 0;
+  for (size_t p = 0; p < h->peers.size(); ++p) {
+    if (h->send_counts[p] > 0) {
+      const int k = P.push.npeers++;
+      P.push.peer[k] = h->peers[p];
+      P.push.send_begin[k] = so;
+      P.push.dst_off[k] = send_dst_index[p];
+      P.push.send_begin[k + 1] = so + h->send_counts[p];
+    }
+    so += h->send_counts[p];
+    if (h->recv_counts[p] > 0) P.wait.peer[P.wait.npeers++] = h->peers[p];
+  }
+  // send_rows is laid out peer after peer in plan order; push.send_begin indexes it directly
+  // only if peers without sends contribute nothing, which holds because their count is 0.
+  if (!P.d_tab) FVB_CUDA(cudaMalloc((void **)&P.d_tab, sizeof(PeerTable)));
+  FVB_CUDA(memcpy_sync(h->stream, P.d_tab, &P.tab, sizeof(PeerTable), cudaMemcpyHostToDevice));
+  if (const char *env = getenv("FVB_FUSED_ALLREDUCE")) P.fused = atoi(env) != 0;
+  P.active = true;
   return FVB_OK;
 }
 
@@ -1828,6 +1899,17 @@ int fvb_set_halo_plan(fvb_handle h, int n_peers, const int32_t *peer_ranks, cons
   h->peers.assign(peer_ranks, peer_ranks + n_peers);
   h->send_counts.assign(send_counts, send_counts + n_peers);
   h->recv_counts.assign(recv_counts, recv_counts + n_peers);
+  h->send_first.assign((size_t)n_peers, 0);
+  h->send_contig = true;
+  {
+    int64_t at = 0;
+    for (int p = 0; p < n_peers; ++p) {
+      if (send_counts[p] > 0) h->send_first[(size_t)p] = rows[(size_t)at];
+      for (int64_t k = 1; k < send_counts[p] && h->send_contig; ++k)
+        h->send_contig = rows[(size_t)(at + k)] == rows[(size_t)(at + k - 1)] + 1;
+      at += send_counts[p];
+    }
+  }
   dfree(h, h->send_rows); dfree(h, h->sendbuf);
   FVB_TRY(dalloc(h, &h->send_rows, ns));
   FVB_TRY(dalloc(h, &h->sendbuf, ns));
@@ -1968,27 +2050,7 @@ int fvb_peer_import(fvb_handle h, const uint8_t *blobs, const int64_t *send_dst_
     P.tab.mail[r] = (PeerMail *)P.opened_mail[r];
   }
   P.last_blobs = nb;
-  P.push = HaloPlanDev{};
-  P.wait = HaloPlanDev{};
-  long long so = 0;
-  for (size_t p = 0; p < h->peers.size(); ++p) {
-    if (h->send_counts[p] > 0) {
-      const int k = P.push.npeers++;
-      P.push.peer[k] = h->peers[p];
-      P.push.send_begin[k] = so;
-      P.push.dst_off[k] = send_dst_index[p];
-      P.push.send_begin[k + 1] = so + h->send_counts[p];
-    }
-    so += h->send_counts[p];
-    if (h->recv_counts[p] > 0) P.wait.peer[P.wait.npeers++] = h->peers[p];
-  }
-  // send_rows is laid out peer after peer in plan order; push.send_begin indexes it directly
-  // only if peers without sends contribute nothing, which holds because their count is 0.
-  if (!P.d_tab) FVB_CUDA(cudaMalloc((void **)&P.d_tab, sizeof(PeerTable)));
-  FVB_CUDA(memcpy_sync(h->stream, P.d_tab, &P.tab, sizeof(PeerTable), cudaMemcpyHostToDevice));
-  if (const char *env = getenv("FVB_FUSED_ALLREDUCE")) P.fused = atoi(env) != 0;
-  P.active = true;
-  return FVB_OK;
+  return peer_finish_plan(h, send_dst_index);
 }
 
 int fvb_solve(fvb_handle h, double rtol, int64_t maxiter, const double *x0_free, double *head_nodes, double *x_free,
@@ -2140,6 +2202,22 @@ int fvb_step(fvb_handle h, int rhs_slot, int u_slot, double dt, int out_slot, in
   }
   return FVB_OK;
 }
+int fvb_solve_shifted(fvb_handle h, int rhs_slot, int x0_slot, double sigma, int out_slot, double rtol, int64_t maxiter,
+                      int64_t *iters, int *converged) {
+  FVB_TRY(check_handle(h, true));
+  if (!(sigma >= 0)) return set_error(FVB_ERR_BAD_INPUT, "shift must be non-negative");
+  FVB_TRY(ensure_slot(h, rhs_slot));
+  FVB_TRY(ensure_slot(h, x0_slot));
+  FVB_TRY(ensure_slot(h, out_slot));
+  FVB_TRY(ensure_workspace(h));
+  const int64_t n = h->nf_local;
+  cudaStream_t st = h->stream;
+  FVB_CUDA(cudaMemcpyAsync(h->x, h->slots[x0_slot], sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  FVB_TRY(pcg_run(h, h->slots[rhs_slot], true, sigma, rtol, maxiter, iters, converged));
+  FVB_CUDA(cudaMemcpyAsync(h->slots[out_slot], h->x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+  return FVB_OK;
+}
+
 int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes) {
   FVB_TRY(check_handle(h, true));
   FVB_TRY(ensure_slot(h, slot));
@@ -2350,3 +2428,5 @@ int fvb_sync(fvb_handle h) {
 }
 
 }  // extern "C"
+
+#include "multi_impl.h"

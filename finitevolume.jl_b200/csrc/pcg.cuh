@@ -95,32 +95,57 @@ k_pcg_init(int64_t n, const double *__restrict__ rhs, const double *__restrict__
   s0 = block_sum(s0);
   s1 = block_sum(s1);
   double t0, t1;
-  if (last_block_sum2(s0, s1, partials, ticket, &t0, &t1)) {
-    double v[2] = {t0, t1};
-    const bool ok = finalize_mode != 2 || peer_allreduce_thread(pr, v, 2, scal);  // 2: sum over the ranks here
-    scal->red[0] = v[0]; scal->red[1] = v[1];
-    if (ok && finalize_mode >= 1) pcg_finish_init(scal, v[0], v[1]);
+  if (last_block_sum2_all(s0, s1, partials, ticket, &t0, &t1) && threadIdx.x < 32) {
+    double v[2] = {t0, t1};  // valid in lane 0
+    const bool ok = finalize_mode != 2 || peer_allreduce_warp(pr, v, 2, scal);  // 2: sum over the ranks here
+    if (threadIdx.x == 0) {
+      scal->red[0] = v[0]; scal->red[1] = v[1];
+      if (ok && finalize_mode >= 1) pcg_finish_init(scal, v[0], v[1]);
+    }
   }
 }
 
 // x += alpha_prev * u (the deferred update of the previous iteration); u = dinv .* r + beta * u
 // SC: u^ = r^ + beta * u^ (dinv is not read)
+// fp.npeers > 0 (slab partitions over NVLink peer memory): the thread that produces u[i] of a boundary row also
+// stores it into the neighbour's halo slot, and the CTA drawing the last ticket raises the neighbours' flags --
+// the halo exchange of the next product rides on this kernel instead of a launch of its own (peer.cuh).
 template <bool SC>
 __global__ void __launch_bounds__(kBlock)
 k_update_u(int64_t n, const double *__restrict__ dinv, const double *__restrict__ r, double *__restrict__ u,
-           double *__restrict__ x, const PcgScal *__restrict__ scal) {
+           double *__restrict__ x, const PcgScal *__restrict__ scal, FusedPush fp, unsigned int *ticket) {
   if (scal->done) return;
   const bool first = scal->iter == 0;
   const double beta = first ? 0.0 : scal->rho / scal->rho_prev;
   const double ap = scal->alpha_prev;
-  if (first) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-      u[i] = SC ? r[i] : dinv[i] * r[i];
-  } else {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double un;
+    if (first) {
+      un = SC ? r[i] : dinv[i] * r[i];
+    } else {
       const double ui = u[i];
       x[i] += ap * ui;
-      u[i] = (SC ? r[i] : dinv[i] * r[i]) + beta * ui;
+      un = (SC ? r[i] : dinv[i] * r[i]) + beta * ui;
+    }
+    u[i] = un;
+    if (fp.npeers > 0) {
+      const long long k0 = i - fp.begin[0];
+      if (k0 >= 0 && k0 < fp.count[0]) fp.dst[0][k0] = un;
+      if (fp.npeers > 1) {
+        const long long k1 = i - fp.begin[1];
+        if (k1 >= 0 && k1 < fp.count[1]) fp.dst[1][k1] = un;
+      }
+    }
+  }
+  if (fp.npeers > 0) {
+    __threadfence_system();  // my remote stores are visible system-wide before the ticket
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (last && (int)threadIdx.x < fp.npeers) {
+      __threadfence_system();
+      st_release_sys(fp.flag[threadIdx.x], fp.seq);
     }
   }
 }
@@ -148,11 +173,13 @@ k_update_xr(int64_t n, const double *__restrict__ c, const double *__restrict__ 
   s0 = block_sum(s0);
   s1 = block_sum(s1);
   double t0, t1;
-  if (last_block_sum2(s0, s1, partials, ticket, &t0, &t1)) {
-    double v[2] = {t0, t1};
-    const bool ok = finalize_mode != 2 || peer_allreduce_thread(pr, v, 2, scal);
-    scal->red[0] = v[0]; scal->red[1] = v[1];
-    if (ok && finalize_mode >= 1) pcg_finish_iter(scal, v[0], v[1], hist);
+  if (last_block_sum2_all(s0, s1, partials, ticket, &t0, &t1) && threadIdx.x < 32) {
+    double v[2] = {t0, t1};  // valid in lane 0
+    const bool ok = finalize_mode != 2 || peer_allreduce_warp(pr, v, 2, scal);
+    if (threadIdx.x == 0) {
+      scal->red[0] = v[0]; scal->red[1] = v[1];
+      if (ok && finalize_mode >= 1) pcg_finish_iter(scal, v[0], v[1], hist);
+    }
   }
 }
 

@@ -81,4 +81,54 @@ __device__ __forceinline__ bool peer_allreduce_thread(const PeerRed &pr, double 
   return true;
 }
 
+// The same all-reduce executed by the first WARP of the CTA that folded this rank's partials (all 32 lanes must
+// call it, converged; v is valid in lane 0 on entry and in every lane on return): lane q writes this rank's sums
+// into rank q's mailbox, fences and raises rank q's flag, then waits for rank q's contribution -- the eight
+// remote store/fence/flag sequences and the eight waits overlap instead of running back to back in one thread.
+__device__ __forceinline__ bool peer_allreduce_warp(const PeerRed &pr, double *v, int count, PcgScal *scal) {
+  const PeerTable &T = *pr.tab;
+  const int lane = threadIdx.x & 31;
+  const int par = (int)(pr.seq & 1ull);
+  for (int i = 0; i < count; ++i) v[i] = __shfl_sync(0xffffffffu, v[i], 0);
+  PeerMail *mine = T.mail[T.rank];
+  bool ok = true;
+  if (lane < T.nranks) {
+    PeerMail *dst = T.mail[lane];
+    for (int i = 0; i < count; ++i) dst->vals[par][T.rank][i] = v[i];
+    __threadfence_system();
+    st_release_sys(&dst->vseq[par][T.rank], pr.seq);
+    ok = wait_flag(&mine->vseq[par][lane], pr.seq);
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (!ok) {
+    if (lane == 0) { mine->error = 1; scal->done = 1; scal->converged = 0; }
+    return false;
+  }
+  for (int i = 0; i < count; ++i) {
+    double s = 0.0;
+    for (int r = 0; r < T.nranks; ++r) s += *(volatile double *)&mine->vals[par][r][i];
+    v[i] = s;
+  }
+  return true;
+}
+
+// Halo push fused into the kernel that produces the search direction (pcg.cuh: k_update_u): slab partitions send
+// contiguous row ranges (the first / last plane), so the thread that writes u[i] also stores it into the
+// neighbour's halo slot; the CTA drawing the last ticket raises the neighbours' flags.  npeers = 0: nothing fused.
+struct FusedPush {
+  int npeers;
+  double *dst[2];                // neighbour's vector, already offset to this rank's first halo slot there
+  long long begin[2], count[2];  // my rows [begin, begin + count)
+  unsigned long long *flag[2];   // &neighbour_mailbox->hseq[my rank]
+  unsigned long long seq;
+};
+// Halo wait fused into the SpMV (dia_tma.cuh): only the tiles at the slab ends read halo values, they are dealt
+// last, and a CTA spins on the (local) flags right before its first such tile.  n = 0: nothing to wait for.
+struct FusedWait {
+  int n;
+  const unsigned long long *flag[2];  // &my_mailbox->hseq[neighbour]
+  unsigned long long seq;
+  int *error;                         // &my_mailbox->error
+};
+
 }  // namespace fvb

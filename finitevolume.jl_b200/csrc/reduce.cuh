@@ -76,4 +76,44 @@ __device__ __forceinline__ bool last_block_sum2(double a, double b, double *part
   return threadIdx.x == 0;
 }
 
+// Variants for kernels that finish their sums across the GPUs with the first warp (peer_base.cuh:
+// peer_allreduce_warp): every thread of the block learns whether this block drew the last ticket; the totals are
+// valid in thread 0.
+__device__ __forceinline__ bool last_block_sum1_all(double mine, double *partials, unsigned int *ticket, double *total) {
+  __shared__ bool is_last1a;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = mine;
+    __threadfence();
+    is_last1a = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last1a) return false;
+  __threadfence();
+  double s = 0.0;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += __ldcg(&partials[i]);
+  *total = block_sum(s);
+  return true;
+}
+__device__ __forceinline__ bool last_block_sum2_all(double a, double b, double *partials, unsigned int *ticket,
+                                                    double *ta, double *tb) {
+  __shared__ bool is_last2a;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = a;
+    partials[gridDim.x + blockIdx.x] = b;
+    __threadfence();
+    is_last2a = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last2a) return false;
+  __threadfence();
+  double s = 0.0, q = 0.0;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+    s += __ldcg(&partials[i]);
+    q += __ldcg(&partials[gridDim.x + i]);
+  }
+  *ta = block_sum(s);
+  *tb = block_sum(q);
+  return true;
+}
+
 }  // namespace fvb

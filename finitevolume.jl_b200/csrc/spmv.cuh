@@ -142,12 +142,15 @@ k_spmv(int nrows, const int *__restrict__ rowptr, const int *__restrict__ colidx
       consumer_sync();
       if ((t & 31) == 0) S.wsum[t >> 5] = q;
       consumer_sync();
-      if (t == 0) {
+      if (t < 32) {
         double tot = 0.0;
-        for (int w = 0; w < kSpmvRows / 32; ++w) tot += S.wsum[w];
-        const bool ok = finalize_mode != 2 || peer_allreduce_thread(pr, &tot, 1, scal);
-        scal->red[0] = tot;
-        if (ok && finalize_mode >= 1) scal->uc = tot;
+        if (t == 0)
+          for (int w = 0; w < kSpmvRows / 32; ++w) tot += S.wsum[w];
+        const bool ok = finalize_mode != 2 || peer_allreduce_warp(pr, &tot, 1, scal);
+        if (t == 0) {
+          scal->red[0] = tot;
+          if (ok && finalize_mode >= 1) scal->uc = tot;
+        }
       }
     }
   }

@@ -220,6 +220,13 @@ int fvb_set_storage(fvb_handle h, double Ss, const double *volumes_owned_nodes);
  * reference does (:73).  Returns FVB_ERR_BAD_INPUT for dt <= 0 (:68-70). */
 int fvb_step(fvb_handle h, int rhs_slot, int u_slot, double dt, int out_slot, int adjoint,
              double rtol, int64_t maxiter, int64_t *iters, int *converged);
+/* The `linearsolver(A, rhs, x0)` hook of backwardeulerintegrate (src/transient.jl:136, default :50-58) on the
+ * resident matrix: solves (A + sigma * D) x = rhs_slot starting from x0_slot (cg!-style warm start, tolerance
+ * relative to the initial residual), D as set by fvb_set_storage (identity if unset).  The reference hands the
+ * hook A~ = D^-1 A + I/dt and rhs~ = D^-1 b + u/dt; the equivalent SPD system is (A + D/dt) x = D .* rhs~, so a
+ * shim passes sigma = 1/dt and rhs = D .* rhs~ (julia/FiniteVolumeB200.jl: linearsolver). */
+int fvb_solve_shifted(fvb_handle h, int rhs_slot, int x0_slot, double sigma, int out_slot, double rtol,
+                      int64_t maxiter, int64_t *iters, int *converged);
 /* Scatter a free-row slot to owned nodes (freenodes2nodes, src/transient.jl:172). */
 int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes);
 
@@ -299,6 +306,42 @@ typedef struct {
 int fvb_set_profiling(fvb_handle h, int stride);
 int fvb_get_timings(fvb_handle h, fvb_timings *out);
 int fvb_sync(fvb_handle h);
+
+/* ---- single-process multi-GPU front end -------------------------------------------------------
+ * The reference is ONE single-threaded Julia process: a drop-in lets that one thread make one call and
+ * have the solve run on all the GPUs of the box -- no torchrun, no MPI.  An fvb_multi owns one handle
+ * per device and drives them from worker threads it creates per call (the caller's thread blocks, like
+ * any ccall).  The whole problem is passed exactly as to solvediffusion (src/FiniteVolume.jl:157), as
+ * HOST arrays; the library partitions it into contiguous node ranges (whole x-planes balanced by free
+ * planes when the face list is regulargrid's -- each device then gets exactly regulargrid's slab list,
+ * one contiguous block copied straight from the caller's arrays -- otherwise equal node counts with the
+ * faces filtered on the host), builds the halo plan itself and maps the devices' vectors by
+ * cudaDeviceEnablePeerAccess (halo planes and CG scalars travel over NVLink peer memory, as in the
+ * one-process-per-GPU mode; no CUDA IPC).  ndev = 1 is the plain single-GPU path.
+ *   device_ids   NULL for 0..ndev-1; a device may appear only once
+ *   head_nodes   all N nodes (host); x_free all Nf free rows (host); either may be NULL
+ * fvb_multi_get_csr returns the WHOLE matrix (ptr[Nf+1], idx/val[nnz], 1-based) = SparseMatrixCSC A. */
+typedef struct fvb_multi_s *fvb_multi;
+int fvb_multi_create(int ndev, const int *device_ids, fvb_multi *out);
+int fvb_multi_destroy(fvb_multi m);
+int fvb_multi_set_preconditioner(fvb_multi m, int kind, int nu, double omega, double oc);
+int fvb_multi_assemble(fvb_multi m, int64_t n_nodes, int64_t n_faces, const int64_t *neighbors, const double *aol,
+                       const double *cond, int64_t n_cond, const int64_t *metaindex, int logk,
+                       const double *sources, int64_t n_dirichlet, const int64_t *dnodes, const double *dheads);
+/* grid-implicit variant (see fvb_assemble_regulargrid): nodehycos = all N node values, sources all N or NULL */
+int fvb_multi_assemble_regulargrid(fvb_multi m, const double mins[3], const double maxs[3], const int64_t ns[3],
+                                   const double *nodehycos, int logmean, int logk, const double *sources,
+                                   int64_t n_dirichlet, const int64_t *dnodes, const double *dheads);
+/* node_lo/node_hi: ndev entries each (1-based inclusive range of every device), or NULL */
+int fvb_multi_sizes(fvb_multi m, int64_t *nf_global, int64_t *nnz_global, int *ndev, int64_t *node_lo,
+                    int64_t *node_hi);
+int fvb_multi_solve(fvb_multi m, double rtol, int64_t maxiter, double *head_nodes, double *x_free,
+                    int64_t *iters, int *converged, double *resnorm_hist, int64_t hist_cap);
+int fvb_multi_get_csr(fvb_multi m, int64_t *ptr, int64_t *idx, double *val);
+int fvb_multi_get_b(fvb_multi m, double *b);
+int fvb_multi_get_freenode(fvb_multi m, uint8_t *freenode);
+/* the per-device handle (owned by m) for anything else: timings, formats, values-only updates */
+int fvb_multi_device_handle(fvb_multi m, int i, fvb_handle *out);
 
 #ifdef __cplusplus
 }

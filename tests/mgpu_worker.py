@@ -87,8 +87,11 @@ def main():
         hmg = np.concatenate([o[7] for o in out])
         err_mg = np.max(np.abs(hmg - ho)) / np.max(np.abs(ho))
         # distributed V-cycle: iteration count must stay in the single-GPU class, far below Jacobi
-        mg_ok = (err_mg <= 1e-8 and all(o[9] for o in out) and len({o[8] for o in out}) == 1
-                 and all(o[10] == "mg" for o in out) and out[0][8] * 3 < out[0][2])
+        # (partitions with a rank that owns no free row, or a single plane, cannot build the hierarchy: every rank
+        #  then agrees on Jacobi and only the heads are checked -- FV_EXPECT_MG=0)
+        expect_mg = os.environ.get("FV_EXPECT_MG", "1") == "1"
+        mg_ok = (err_mg <= 1e-8 and all(o[9] for o in out) and len({o[8] for o in out}) == 1 and len({o[10] for o in out}) == 1
+                 and (not expect_mg or (all(o[10] == "mg" for o in out) and out[0][8] * 3 < out[0][2])))
         iters = {o[2] for o in out}
         hun = np.concatenate([o[12] for o in out])
         sc_ok = (len({o[11] for o in out}) == 1 and np.max(np.abs(hun - ho)) <= 1e-8 * np.max(np.abs(ho))
