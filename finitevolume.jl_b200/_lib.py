@@ -24,7 +24,7 @@ SYMBOLS = [
     "fvb_step", "fvb_vec_to_nodes", "fvb_time_spmv", "fvb_device_alloc", "fvb_device_free", "fvb_device_copy", "fvb_regulargrid",
     "fvb_nodehycos2neighborhycos", "fvb_set_preconditioner", "fvb_get_preconditioner", "fvb_set_spmv_format", "fvb_get_spmv_format", "fvb_set_pcg_scaling", "fvb_get_pcg_scaling", "fvb_set_profiling", "fvb_get_timings", "fvb_sync",
     "fvb_set_assembly", "fvb_get_assembly", "fvb_assemble_regulargrid",
-    "fvb_solve_shifted", "fvb_multi_create", "fvb_multi_destroy", "fvb_multi_set_preconditioner", "fvb_multi_assemble",
+    "fvb_solve_shifted", "fvb_integrate", "fvb_multi_create", "fvb_multi_destroy", "fvb_multi_set_preconditioner", "fvb_multi_assemble",
     "fvb_multi_assemble_regulargrid", "fvb_multi_sizes", "fvb_multi_solve", "fvb_multi_get_csr", "fvb_multi_get_b",
     "fvb_multi_get_freenode", "fvb_multi_device_handle",
 ]
@@ -34,6 +34,16 @@ class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("assemble_ms", C.c_double), ("solve_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("spmv_ms_total", C.c_double), ("spmv_samples", C.c_int64),
                 ("kernel_launches", C.c_int64)]
+
+
+GETB_FN = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.c_void_p)
+STEP_CALLBACK_FN = C.CFUNCTYPE(None, C.c_double, C.c_double, C.c_void_p)
+
+
+class IntegrateOptions(C.Structure):
+    _fields_ = [("atol", C.c_double), ("dt0", C.c_double), ("fixed_step", C.c_int), ("adjoint", C.c_int),
+                ("rtol", C.c_double), ("maxiter", C.c_int64), ("getb", GETB_FN), ("getb_ctx", C.c_void_p),
+                ("callback", STEP_CALLBACK_FN), ("callback_ctx", C.c_void_p)]
 
 
 class FVBError(RuntimeError):

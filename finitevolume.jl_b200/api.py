@@ -360,6 +360,44 @@ class System:
                              C.byref(conv)))
         return int(iters.value), bool(conv.value)
 
+    def integrate(self, u0_free, t0, tfinal, dt0=1.0, atol=1e-4, fixed_step=False, adjoint=False, rtol=SQRT_EPS,
+                  maxiter=DEFAULT_MAXITER, getb=None, callback=None, want="free", max_states=4096):
+        """fvb_integrate: the reference's whole backwardeulerintegrate loop (src/transient.jl:78-154) behind one call.
+        getb(t) -> UNSCALED right-hand side on the free rows (None: the assembled b); callback(t, dt) per attempted
+        step.  want: "free" (states on free rows), "heads" (through freenodes2nodes) or None (times only).
+        -> (states [n_states, ...] or None, ts, stats)."""
+        nf = self.sizes()["nf_local"]
+        u0 = f64(u0_free).reshape(-1)
+        if u0.size != nf:
+            raise ValueError("u0 must hold the free rows")
+        keep = []
+        opt = _lib.IntegrateOptions(atol=float(atol), dt0=float(dt0), fixed_step=int(bool(fixed_step)), adjoint=int(bool(adjoint)),
+                                    rtol=float(rtol), maxiter=int(maxiter))
+        if getb is not None:
+            def _getb(t, out, _ctx):
+                np.ctypeslib.as_array(out, shape=(max(nf, 1),))[:nf] = np.asarray(getb(t), np.float64).reshape(-1)
+            opt.getb = _lib.GETB_FN(_getb)
+            keep.append(opt.getb)
+        if callback is not None:
+            opt.callback = _lib.STEP_CALLBACK_FN(lambda t, dt, _ctx: callback(t, dt))
+            keep.append(opt.callback)
+        while True:
+            ts = np.empty(max_states, np.float64)
+            width = nf if want == "free" else (self.n_own_nodes if want == "heads" else 0)
+            out = np.empty((max_states, width), np.float64) if width else None
+            ns, nsol, nit, natt = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+            status = lib().fvb_integrate(self._h, ptr(u0), C.c_double(t0), C.c_double(tfinal), C.byref(opt), C.c_int64(max_states),
+                                         ptr(ts), ptr(out) if want == "free" else None, ptr(out) if want == "heads" else None,
+                                         C.byref(ns), C.byref(nsol), C.byref(nit), C.byref(natt))
+            if status == 5 and b"max_states" in lib().fvb_last_error() and callback is None:
+                max_states *= 4  # more accepted steps than room: rerun with larger buffers
+                continue
+            check(status)
+            break
+        k = ns.value
+        stats = dict(steps=k - 1, linear_solves=nsol.value, cg_iterations=nit.value, attempts=natt.value)
+        return (out[:k] if out is not None else None), ts[:k], stats
+
     def solve_shifted(self, rhs_slot, x0_slot, sigma, out_slot, rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER):
         """(A + sigma D) x = rhs from x0, slot -> slot: the reference's linearsolver(A, rhs, x0) hook
         (src/transient.jl:136) on the resident matrix."""

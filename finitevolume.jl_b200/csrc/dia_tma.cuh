@@ -40,6 +40,7 @@ constexpr int kDiaTmaMaxStages = 3;
 constexpr int kDiaTmaCtasPerSm = 1;
 constexpr int kDiaNearMax = kDiaTmaTile / 2;            // offsets up to here are served by the centre slices
 constexpr int kDiaTmaSmemMax = 227 * 1024;              // dynamic shared memory one CTA may opt in to
+constexpr int kDiaBlockRows = 262144;                   // rows of one plane swept together when planes are larger
 
 // Per-stage layout in doubles (filled on the host: dia_tma_layout).
 struct DiaTmaLayout {
@@ -56,6 +57,8 @@ struct DiaTmaLayout {
   int bar_off;       // byte offset of the mbarriers / reduction scratch behind the stages
   uint32_t tx_bytes; // bytes one interior tile brings in
   int64_t reach;     // interior tiles satisfy r0 >= reach and r0 + T + reach <= nf
+  int blk_tpp;       // plane-blocked tile order (DiaTileOrder): tiles per plane-distance offset, 0 = off
+  int blk_yb;        // tiles of one plane that form a block (a divisor of blk_tpp)
 };
 
 inline int dia_even_up(int64_t o) { return (int)((o + 1) & ~(int64_t)1); }
@@ -93,6 +96,18 @@ inline DiaTmaLayout dia_tma_layout(int K, const int64_t *off, bool unit) {
     if ((size_t)st * p * 8 + dia_tma_tail_bytes() <= (size_t)kDiaTmaSmemMax) L.stages = st;
   L.bar_off = std::max(L.stages, 1) * p * 8;
   L.reach = reach;
+  // Plane-blocked sweep for big planes.  The plane-distance re-reads (x[r +- o], the lower plane diagonal) are L2
+  // hits only while two planes' worth of streams (2 * o rows * ~40 B) fit in L2: true at 512^2 rows per plane
+  // (21 MB), not at 1024^2 (84 MB against a 2 x 63 MB L2).  Then the tiles of a plane are cut into blocks of
+  // blk_yb tiles and the sweep runs through ALL planes of one block before moving to the next block, which
+  // brings the re-use distance back to 2 * blk_yb tiles.
+  L.blk_tpp = L.blk_yb = 0;
+  if (K >= 2 && off[K - 1] > kDiaBlockRows && off[K - 1] % T == 0) {
+    const int tpp = (int)(off[K - 1] / T);
+    int yb = kDiaBlockRows / T;
+    while (yb > 1 && tpp % yb) --yb;
+    if (yb >= 32) { L.blk_tpp = tpp; L.blk_yb = yb; }
+  }
   return L;
 }
 inline size_t dia_tma_smem_bytes(const DiaTmaLayout &L) { return (size_t)L.bar_off + dia_tma_tail_bytes(); }
@@ -102,22 +117,36 @@ __device__ __forceinline__ void dia_consumer_sync() { asm volatile("bar.sync 1, 
 // Tiles are dealt in the order "interior first, edge tiles last": the tiles at the two ends of the owned range
 // are the only ones that read halo values, so a multi-GPU product can start on its interior while the neighbours'
 // planes are still in flight and wait for them (FusedWait) only when it gets there.
+// Big planes (L.blk_tpp > 0): the interior tiles are additionally taken block by block -- all planes of the
+// first blk_yb tiles of a plane, then all planes of the next blk_yb tiles, ... (see dia_tma_layout).
 struct DiaTileOrder {
   int first_int, n_int;  // interior tiles are first_int .. first_int + n_int - 1
+  int tpp, yb, n_blk;    // blocked part: the first n_blk = (n_int / tpp) * tpp interior tiles (0: no blocking)
   __device__ __forceinline__ int operator()(int v) const {
-    if (v < n_int) return first_int + v;
+    if (v < n_int) {
+      if (v < n_blk) {
+        const int np = n_blk / tpp;            // planes
+        const int per_block = np * yb;
+        const int b = v / per_block, rem = v - b * per_block;
+        const int p = rem / yb, j = rem - p * yb;
+        return first_int + p * tpp + b * yb + j;
+      }
+      return first_int + v;
+    }
     const int e = v - n_int;
     return e < first_int ? e : e + n_int;
   }
 };
-__device__ __forceinline__ DiaTileOrder dia_tile_order(int nrows, int64_t reach) {
+__device__ __forceinline__ DiaTileOrder dia_tile_order(int nrows, const DiaTmaLayout &L) {
   constexpr int T = kDiaTmaTile;
   DiaTileOrder o;
-  const int64_t first = (reach + T - 1) / T;
-  const int64_t last = ((int64_t)nrows - T - reach) >= 0 ? ((int64_t)nrows - T - reach) / T : -1;
+  const int64_t first = (L.reach + T - 1) / T;
+  const int64_t last = ((int64_t)nrows - T - L.reach) >= 0 ? ((int64_t)nrows - T - L.reach) / T : -1;
   o.first_int = (int)first;
   o.n_int = last >= first ? (int)(last - first + 1) : 0;
   if (o.n_int == 0) o.first_int = 0;
+  o.tpp = L.blk_tpp; o.yb = L.blk_yb;
+  o.n_blk = (L.blk_tpp > 0 && o.n_int >= 2 * L.blk_tpp) ? (o.n_int / L.blk_tpp) * L.blk_tpp : 0;
   return o;
 }
 
@@ -164,7 +193,7 @@ k_spmv_dia_tma(int nrows, DiaDesc D, DiaTmaLayout L, const double *__restrict__ 
   int *const is_last = reinterpret_cast<int *>(wsum + kDiaTmaRows / 32);
   const int t = threadIdx.x;
   const int ntiles = (nrows + T - 1) / T;
-  const DiaTileOrder order = dia_tile_order(nrows, L.reach);
+  const DiaTileOrder order = dia_tile_order(nrows, L);
   if (t == 0) {
     for (int s = 0; s < nstages; ++s) {
       mbar_init(&full[s], 1);

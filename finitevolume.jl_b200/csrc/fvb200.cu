@@ -13,6 +13,7 @@
 #include "assemble.cuh"
 #include "box.cuh"
 #include "common.cuh"
+#include "coop.cuh"
 #include "dia.cuh"
 #include "dia_tma.cuh"
 #include "grid.cuh"
@@ -213,7 +214,7 @@ int halo_exchange(fvb_handle h, double *vec, bool pushed = false, FusedWait *def
         defer->seq = seq;
         defer->error = &P.mail->error;
       } else {
-        k_halo_wait<<<1, 32, 0, h->stream>>>(P.mail, P.wait, seq, h->scal);
+        k_halo_wait<<<1, 32, 0, h->stream>>>(P.mail, P.wait, seq, h->scal, pushed ? 1 : 0);
         h->tm.kernel_launches++;
       }
     }
@@ -2232,6 +2233,257 @@ int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   dfree(h, d_head);
   if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+  return FVB_OK;
+}
+
+// ---- device-resident integrator (src/transient.jl:78-154) ----------------------------------------------------------
+}  // extern "C" (helpers below are internal)
+
+namespace {
+
+// The step controller of the reference -- backwardeulertwostep! (:78-87), adaptivebackwardeulerstep! (:89-121),
+// fixedbackwardeulerstep! (:130-134) and the outer loop (:136-154) -- driving device-resident vectors.  Small
+// single-GPU systems run every step-doubling attempt (up to three solves + the error norm) as ONE cooperative
+// kernel (coop.cuh); everything else goes through fvb_step / fvb_vec_diffnorm, one call per solve.
+struct Integrator {
+  fvb_handle h;
+  const fvb_integrate_options *opt;
+  bool coop = false;
+  int coop_grid = 0;
+  double *work[6] = {};      // x, r, p, c, dinv, rhs of the cooperative kernel
+  double *coop_partials = nullptr, *coop_result = nullptr;
+  double *result_host = nullptr;
+  std::vector<int> free_slots;
+  int b_slot = 0;
+  int64_t solves = 0, cg_its = 0, attempts = 0;
+  bool all_converged = true;
+
+  int take() { int s = free_slots.back(); free_slots.pop_back(); return s; }
+  void give(int s) { if (s >= 0) free_slots.push_back(s); }
+
+  int load_b(double t) {
+    if (!opt->getb) return FVB_OK;  // constant b, loaded once by the caller
+    std::vector<double> hb((size_t)std::max<int64_t>(h->nf_local, 1));
+    opt->getb(t, hb.data(), opt->getb_ctx);
+    return fvb_vec_upload(h, b_slot, hb.data());
+  }
+
+  // one backward-Euler solve through the general path
+  int onestep(int u, double t, double dt, int out) {
+    if (!(dt > 0)) return set_error(FVB_ERR_BAD_INPUT, "time step must be positive");
+    FVB_TRY(load_b(t));
+    int64_t it = 0;
+    int conv = 0;
+    FVB_TRY(fvb_step(h, b_slot, u, dt, out, opt->adjoint, opt->rtol, opt->maxiter, &it, &conv));
+    ++solves; cg_its += it; all_converged = all_converged && conv;
+    return FVB_OK;
+  }
+
+  int launch_coop(int nsolves, const CoopSolve *sv, int na, int nb, double *err) {
+    CoopJob J = {};
+    J.nsolves = nsolves;
+    for (int q = 0; q < nsolves; ++q) J.s[q] = sv[q];
+    J.na = na >= 0 ? h->slots[na] : nullptr;
+    J.nb = nb >= 0 ? h->slots[nb] : nullptr;
+    J.adjoint = opt->adjoint;
+    J.rtol = opt->rtol;
+    J.maxiter = opt->maxiter;
+    J.n = (int)h->nf_local;
+    if (h->dia_on && h->fmt_request != 1) {
+      J.D.K = h->dia_K;
+      for (int k = 0; k < kDiaMaxOff; ++k) { J.D.off[k] = h->dia_off[k]; J.D.U[k] = h->dia_U[k]; }
+      J.D.diag = h->diag; J.D.row_start = h->row_start; J.D.nf = h->nf_local;
+    } else {
+      J.rowptr = h->rowptr; J.colidx = h->colidx; J.vals = h->vals;
+    }
+    J.diag = h->diag; J.Dvec = h->Dvec;
+    J.x = work[0]; J.r = work[1]; J.p = work[2]; J.c = work[3]; J.dinv = work[4]; J.rhs = work[5];
+    J.partials = coop_partials;
+    J.result = coop_result;
+    void *args[] = {&J};
+    FVB_CUDA(cudaLaunchCooperativeKernel((void *)k_coop_attempt, dim3((unsigned)coop_grid), dim3(kBlock), args, 0, h->stream));
+    h->tm.kernel_launches++;
+    FVB_CUDA(cudaMemcpyAsync(result_host, coop_result, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FVB_CUDA(cudaStreamSynchronize(h->stream));
+    if (err) *err = result_host[0];
+    solves += nsolves;
+    cg_its += (int64_t)result_host[1];
+    all_converged = all_converged && result_host[2] != 0.0;
+    return FVB_OK;
+  }
+
+  // backwardeulertwostep!(..., onestep = given or computed): returns the new state's slot (*res), the time actually
+  // stepped and whether the step size may grow.  `one` < 0: compute the full step here.  Consumes `one`.
+  int twostep(int u, double t, double dt, int one, int *res, double *laststep, bool *increase) {
+    if (!(dt > 0)) return set_error(FVB_ERR_BAD_INPUT, "time step must be positive");
+    ++attempts;
+    const int h1 = take(), two = take();
+    double err = 0.0;
+    if (coop) {
+      CoopSolve sv[3];
+      int q = 0;
+      if (one < 0) {
+        one = take();
+        sv[q++] = CoopSolve{h->slots[b_slot], h->slots[u], h->slots[one], 1.0 / dt};
+      }
+      sv[q++] = CoopSolve{h->slots[b_slot], h->slots[u], h->slots[h1], 1.0 / (0.5 * dt)};
+      sv[q++] = CoopSolve{h->slots[b_slot], h->slots[h1], h->slots[two], 1.0 / (0.5 * dt)};
+      FVB_TRY(launch_coop(q, sv, one, two, &err));
+    } else {
+      if (one < 0) {
+        one = take();
+        FVB_TRY(onestep(u, t, dt, one));
+      }
+      FVB_TRY(onestep(u, t, 0.5 * dt, h1));
+      FVB_TRY(onestep(h1, t + 0.5 * dt, 0.5 * dt, two));
+      FVB_TRY(fvb_vec_diffnorm(h, one, two, &err));
+    }
+    give(one);
+    if (err < opt->atol) {
+      give(h1);
+      *res = two; *laststep = dt; *increase = err < opt->atol / 4;
+    } else {
+      give(two);
+      *res = h1; *laststep = 0.5 * dt; *increase = false;
+    }
+    return FVB_OK;
+  }
+
+  // adaptivebackwardeulerstep! (:89-121).  u stays owned by the caller; *res is a fresh slot.
+  int adaptive(int u, double t, double dt, int *res, double *laststep, bool *increase) {
+    if (opt->callback) opt->callback(t, dt, opt->callback_ctx);
+    int u_new = -1;
+    FVB_TRY(twostep(u, t, dt, -1, &u_new, laststep, increase));
+    if (*laststep < dt) {  // it could not take the step we asked: cover dt with smaller ones
+      bool failed = true;
+      double elapsed = 0.0, target = *laststep;
+      int u_el = u;  // not owned while it equals u
+      while (elapsed < dt) {
+        if (opt->callback) opt->callback(t, dt, opt->callback_ctx);
+        int nxt = -1;
+        // after a failed attempt the half step it returned serves as the full step of the next one (:100-101)
+        FVB_TRY(twostep(u_el, t + elapsed, target, failed ? u_new : -1, &nxt, laststep, increase));
+        if (!failed) give(u_new);
+        u_new = nxt;
+        if (*laststep == target) {
+          elapsed += *laststep;
+          if (u_el != u) give(u_el);
+          // the accepted state is both the new starting point and (if the loop ends here) the result: keep one
+          // slot for each role
+          u_el = take();
+          FVB_TRY(fvb_vec_copy(h, u_el, u_new));
+          if (*increase) target = 2 * *laststep;
+          failed = false;
+        } else if (*laststep < target) {
+          target = *laststep;
+          failed = true;
+        } else {
+          return set_error(FVB_ERR_STATE, "Code is broken -- laststeptime should never be greater than targetdt");
+        }
+        target = std::min(target, dt - elapsed);
+      }
+      if (u_el != u) give(u_el);
+    }
+    *res = u_new;
+    return FVB_OK;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int fvb_integrate(fvb_handle h, const double *u0_free, double t0, double tfinal, const fvb_integrate_options *opt,
+                  int64_t max_states, double *ts, double *us_free, double *heads_nodes, int64_t *n_states,
+                  int64_t *n_solves, int64_t *n_cg_iterations, int64_t *n_attempts) {
+  FVB_TRY(check_handle(h, true));
+  if (!opt || !u0_free || !ts || max_states < 1) return set_error(FVB_ERR_BAD_INPUT, "bad arguments");
+  if (!(opt->dt0 > 0)) return set_error(FVB_ERR_BAD_INPUT, "time step must be positive");
+  FVB_TRY(ensure_workspace(h));
+  const int64_t n = h->nf_local;
+  cudaStream_t st = h->stream;
+  Integrator I;
+  I.h = h;
+  I.opt = opt;
+  for (int s = FVB_NSLOT - 1; s >= 1; --s) I.free_slots.push_back(s);
+  for (int s = 0; s < FVB_NSLOT; ++s) FVB_TRY(ensure_slot(h, s));
+  I.b_slot = 0;
+  if (!opt->getb) {
+    if (opt->adjoint) FVB_CUDA(cudaMemsetAsync(h->slots[0], 0, sizeof(double) * (size_t)std::max<int64_t>(n, 1), st));
+    else FVB_TRY(fvb_vec_load_b(h, 0));
+  }
+  // the one-launch-per-attempt path: single GPU, small system, constant right-hand side
+  const bool dia = h->dia_on && h->fmt_request != 1;
+  I.coop = h->nranks == 1 && n >= 1 && n <= kCoopMaxRows && !opt->getb && !getenv("FVB_COOP_OFF") && (dia || h->rowptr || h->box);
+  if (I.coop) {
+    if (!dia) FVB_TRY(ensure_csr(h));
+    int coop_ok = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, h->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_coop_attempt, kBlock, 0);
+    I.coop = coop_ok && per_sm >= 1;
+    I.coop_grid = std::max(1, std::min(cdiv(n, kBlock), h->num_sms));
+  }
+  auto release = [&]() {
+    for (auto &w : I.work) dfree(h, w);
+    dfree(h, I.coop_partials); dfree(h, I.coop_result);
+    if (I.result_host) cudaFreeHost(I.result_host);
+    I.result_host = nullptr;
+  };
+  if (I.coop) {
+    int s = FVB_OK;
+    for (auto &w : I.work) if (s == FVB_OK) s = dalloc(h, &w, n);
+    if (s == FVB_OK) s = dalloc(h, &I.coop_partials, 3 * (int64_t)I.coop_grid);
+    if (s == FVB_OK) s = dalloc(h, &I.coop_result, 4);
+    if (s == FVB_OK && cudaMallocHost((void **)&I.result_host, 4 * sizeof(double)) != cudaSuccess) s = set_error(FVB_ERR_OOM, "pinned result buffer");
+    if (s != FVB_OK) { release(); return s; }
+  }
+  auto fail = [&](int s) { std::string keep = g_last_error; release(); g_last_error = keep; return s; };
+  // us = [u0], ts = [t0]   (:137-138)
+  int u = I.take();
+  int s = fvb_vec_upload(h, u, u0_free);
+  if (s != FVB_OK) return fail(s);
+  int64_t count = 0;
+  auto store = [&](int slot, double t) -> int {
+    if (count >= max_states) return set_error(FVB_ERR_STATE, "more accepted states than max_states (" + std::to_string(max_states) + "): enlarge the output buffers");
+    ts[count] = t;
+    if (us_free) FVB_CUDA(cudaMemcpyAsync(us_free + count * n, h->slots[slot], sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
+    if (heads_nodes) FVB_TRY(fvb_vec_to_nodes(h, slot, heads_nodes + count * h->n_own_nodes));
+    ++count;
+    return FVB_OK;
+  };
+  if ((s = store(u, t0)) != FVB_OK) return fail(s);
+  double t = t0, dt = std::min(opt->dt0, tfinal - t0);
+  while (t < tfinal) {
+    int nxt = -1;
+    double last = 0.0;
+    bool inc = false;
+    if (opt->fixed_step) {
+      if (opt->callback) opt->callback(t, dt, opt->callback_ctx);
+      nxt = I.take();
+      if (I.coop) {
+        CoopSolve sv{h->slots[I.b_slot], h->slots[u], h->slots[nxt], 1.0 / dt};
+        s = dt > 0 ? I.launch_coop(1, &sv, -1, -1, nullptr) : set_error(FVB_ERR_BAD_INPUT, "time step must be positive");
+      } else {
+        s = I.onestep(u, t, dt, nxt);
+      }
+      last = dt;
+    } else {
+      s = I.adaptive(u, t, dt, &nxt, &last, &inc);
+    }
+    if (s != FVB_OK) return fail(s);
+    I.give(u);
+    u = nxt;
+    t += dt;  // push!(ts, ts[end] + dt)   (:145)
+    if ((s = store(u, t)) != FVB_OK) return fail(s);
+    dt = inc ? std::min(tfinal - t, 2 * last) : std::min(tfinal - t, last);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  release();
+  if (e != cudaSuccess) return set_error(FVB_ERR_CUDA, cudaGetErrorString(e));
+  if (n_states) *n_states = count;
+  if (n_solves) *n_solves = I.solves;
+  if (n_cg_iterations) *n_cg_iterations = I.cg_its;
+  if (n_attempts) *n_attempts = I.attempts;
   return FVB_OK;
 }
 

@@ -114,7 +114,13 @@ template <bool SC>
 __global__ void __launch_bounds__(kBlock)
 k_update_u(int64_t n, const double *__restrict__ dinv, const double *__restrict__ r, double *__restrict__ u,
            double *__restrict__ x, const PcgScal *__restrict__ scal, FusedPush fp, unsigned int *ticket) {
-  if (scal->done) return;
+  if (scal->done) {
+    // iterations enqueued past convergence do no work, but EVERY halo sequence number must still be raised on the
+    // neighbours: a consumer that is not the fused SpMV (k_halo_wait before the per-thread-load or CSR kernels)
+    // waits for it unconditionally
+    if (fp.npeers > 0 && blockIdx.x == 0 && (int)threadIdx.x < fp.npeers) st_release_sys(fp.flag[threadIdx.x], fp.seq);
+    return;
+  }
   const bool first = scal->iter == 0;
   const double beta = first ? 0.0 : scal->rho / scal->rho_prev;
   const double ap = scal->alpha_prev;

@@ -54,7 +54,10 @@ k_halo_push(PeerTable T, HaloPlanDev P, const int *__restrict__ send_rows, const
   }
 }
 
-__global__ void k_halo_wait(PeerMail *mail, HaloPlanDev P, unsigned long long seq, PcgScal *scal) {
+// in_cg: launched inside the CG loop, where iterations enqueued past convergence are no-ops (the producer raises the
+// flag anyway, but there is nothing to wait for).
+__global__ void k_halo_wait(PeerMail *mail, HaloPlanDev P, unsigned long long seq, PcgScal *scal, int in_cg) {
+  if (in_cg && scal->done) return;
   bool ok = true;
   if ((int)threadIdx.x < P.npeers) ok = wait_flag(&mail->hseq[P.peer[threadIdx.x]], seq);
   if (!ok) { mail->error = 1; scal->done = 1; scal->converged = 0; }

@@ -197,19 +197,32 @@ def backwardeulerintegrate_generic(u0, A, b, dt0, t0, tfinal, stepper=adaptiveba
 
 def backwardeulerintegrate(u0, tspan, Ss, volumes, neighbors, areasoverlengths, conductivities, sources,
                            dirichletnodes, dirichletheads, metaindex=None, logtransformconductivity=False, *,
-                           dt0=1.0, stepper=adaptivebackwardeulerstep, atol=1e-4, callback=lambda t, dt: None,
-                           getb=None, rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER, device=0, stats=None):
+                           dt0=1.0, stepper=adaptivebackwardeulerstep, atol=1e-4, callback=None,
+                           getb=None, rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER, device=0, stats=None, controller="device"):
     """Model-level entry, src/transient.jl:156-174 -> (us, ts); every us[i] is a length-N head
     vector (free rows scattered, Dirichlet heads filled in, :172).
 
     getb(t), when given, must return the UNSCALED right-hand side b(t) on the free rows (the
-    reference's getb returns D^-1 b; multiply by Ss*volumes[free] to convert)."""
+    reference's getb returns D^-1 b; multiply by Ss*volumes[free] to convert).
+
+    controller="device" (default): the step controller runs inside the library (fvb_integrate; the two stock
+    steppers of the reference).  controller="host", or any other `stepper` callable: the Python restatement of
+    src/transient.jl:78-154 above drives one fvb_step per solve -- kept as the cross-check of the device one."""
     u0 = np.asarray(u0, np.float64)
     sysm = System(device).assemble(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
                                    metaindex, logtransformconductivity)
     try:
         sysm.set_storage(float(Ss), np.asarray(volumes, np.float64))
         freenode = sysm.freenode()
+        if controller == "device" and stepper in (adaptivebackwardeulerstep, fixedbackwardeulerstep):
+            heads, ts, st = sysm.integrate(u0[freenode], tspan[0], tspan[1], dt0=dt0, atol=atol,
+                                           fixed_step=stepper is fixedbackwardeulerstep, rtol=rtol, maxiter=maxiter,
+                                           getb=getb, callback=callback, want="heads")
+            if stats is not None:
+                stats.update(st)
+            return [heads[k] for k in range(heads.shape[0])], [float(t) for t in ts]
+        if callback is None:
+            callback = lambda t, dt: None  # noqa: E731
         S = DeviceStepper(sysm, getb if getb is not None else (lambda t: None), adjoint=False, rtol=rtol, maxiter=maxiter)
         us, ts = _integrate(S, u0[freenode], dt0, tspan[0], tspan[1], stepper, atol, callback,
                             keep=lambda d: sysm.vec_to_nodes(d.slot))
@@ -223,8 +236,8 @@ def backwardeulerintegrate(u0, tspan, Ss, volumes, neighbors, areasoverlengths, 
 
 def adjointintegrate(getdgdu, tspan, Ss, volumes, neighbors, areasoverlengths, conductivities, sources,
                      dirichletnodes, dirichletheads, metaindex=None, logtransformconductivity=False, *,
-                     dt0=1.0, stepper=adaptivebackwardeulerstep, atol=1e-4, callback=lambda t, dt: None,
-                     rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER, device=0, stats=None):
+                     dt0=1.0, stepper=adaptivebackwardeulerstep, atol=1e-4, callback=None,
+                     rtol=SQRT_EPS, maxiter=DEFAULT_MAXITER, device=0, stats=None, controller="device"):
     """src/transient.jl:188-205 -> (lambdas, ts_lambda): integrates
     dgamma/dt = -(D^-1 A)^T gamma + dg/du(T - t), gamma(0) = 0 and returns it reversed in time,
     lambda(t) = gamma(T - t), on the free rows."""
@@ -233,6 +246,16 @@ def adjointintegrate(getdgdu, tspan, Ss, volumes, neighbors, areasoverlengths, c
     try:
         sysm.set_storage(float(Ss), np.asarray(volumes, np.float64))
         nf = sysm.sizes()["nf_local"]
+        if controller == "device" and stepper in (adaptivebackwardeulerstep, fixedbackwardeulerstep):
+            gam, tsg, st = sysm.integrate(np.zeros(nf), tspan[0], tspan[1], dt0=dt0, atol=atol,
+                                          fixed_step=stepper is fixedbackwardeulerstep, adjoint=True, rtol=rtol, maxiter=maxiter,
+                                          getb=lambda t: np.asarray(getdgdu(tspan[1] - t), np.float64), callback=callback,
+                                          want="free")
+            if stats is not None:
+                stats.update(st)
+            return [gam[k] for k in range(gam.shape[0])][::-1], [tspan[1] - float(t) for t in tsg][::-1]
+        if callback is None:
+            callback = lambda t, dt: None  # noqa: E731
         S = DeviceStepper(sysm, lambda t: np.asarray(getdgdu(tspan[1] - t), np.float64), adjoint=True, rtol=rtol,
                           maxiter=maxiter)
         gammas, tsg = _integrate(S, np.zeros(nf), dt0, tspan[0], tspan[1], stepper, atol, callback,

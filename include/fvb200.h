@@ -227,6 +227,42 @@ int fvb_step(fvb_handle h, int rhs_slot, int u_slot, double dt, int out_slot, in
  * shim passes sigma = 1/dt and rhs = D .* rhs~ (julia/FiniteVolumeB200.jl: linearsolver). */
 int fvb_solve_shifted(fvb_handle h, int rhs_slot, int x0_slot, double sigma, int out_slot, double rtol,
                       int64_t maxiter, int64_t *iters, int *converged);
+/* ---- the whole integrator on the device side of the boundary (src/transient.jl:78-154) ----------
+ * backwardeulerintegrate(u0, A, getb, dt0, t0, tfinal; stepper!, atol, callback) with
+ * stepper! = adaptivebackwardeulerstep! (step doubling: one full step against two half steps,
+ * err = ||one - two||_2 < atol accepts, < atol/4 doubles the step, else the half step is kept and the
+ * step halved, :78-121) or fixedbackwardeulerstep! (:130-134).  State vectors never leave the device
+ * except the accepted ones the caller asks for; on a single GPU and up to 2^20 unknowns with a
+ * constant right-hand side every step-doubling attempt (three warm-started solves + the norm) is
+ * one cooperative kernel launch (csrc/coop.cuh), otherwise one fvb_step per solve.
+ * Call fvb_set_storage first (D = Ss*volumes).  All FVB_NSLOT vector slots are clobbered.
+ *   getb       NULL: the assembled b, constant in time (the model-level entry, :156-163; adjoint:
+ *              zero forcing); else called once per linear solve with the solve's time and must fill
+ *              the UNSCALED right-hand side on the owned free rows (the reference's getb returns
+ *              D^-1 b: multiply by Ss*volumes) -- for the adjoint the forcing dg/du(T - t) (:203)
+ *   callback   NULL or called as callback(t, dt) once per attempted step, as the reference does
+ *   ts         out, [max_states]: t0 and the time of every accepted step (ts[k+1] = ts[k] + dt, :145)
+ *   us_free    out or NULL, [max_states * nf_local]: the accepted states on free rows (us, :144)
+ *   heads_nodes out or NULL, [max_states * n_owned_nodes]: the same through freenodes2nodes (:172)
+ * Fails with FVB_ERR_STATE when more than max_states states are accepted (n_states unchanged). */
+typedef void (*fvb_getb_fn)(double t, double *b_free, void *ctx);
+typedef void (*fvb_step_callback_fn)(double t, double dt, void *ctx);
+typedef struct {
+  double atol;       /* step-doubling tolerance (reference default 1e-4)         */
+  double dt0;        /* first step (reference default 1.0)                        */
+  int fixed_step;    /* 0 adaptivebackwardeulerstep!, 1 fixedbackwardeulerstep!   */
+  int adjoint;       /* 0 forward (:65-76), 1 adjoint operator (:188-205)         */
+  double rtol;       /* linear solves: relative to the warm start's residual     */
+  int64_t maxiter;
+  fvb_getb_fn getb;
+  void *getb_ctx;
+  fvb_step_callback_fn callback;
+  void *callback_ctx;
+} fvb_integrate_options;
+int fvb_integrate(fvb_handle h, const double *u0_free, double t0, double tfinal, const fvb_integrate_options *opt,
+                  int64_t max_states, double *ts, double *us_free, double *heads_nodes, int64_t *n_states,
+                  int64_t *n_solves, int64_t *n_cg_iterations, int64_t *n_attempts);
+
 /* Scatter a free-row slot to owned nodes (freenodes2nodes, src/transient.jl:172). */
 int fvb_vec_to_nodes(fvb_handle h, int slot, double *head_nodes);
 

@@ -17,6 +17,20 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+def _run_group(cmd, env, timeout):
+    """Run a launcher in its own process group and, on timeout, kill the WHOLE group: a killed torchrun parent would
+    otherwise leave its rank processes spinning on the GPUs (and every later measurement on the box polluted)."""
+    import signal
+    p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        os.killpg(p.pid, signal.SIGKILL)
+        out, err = p.communicate()
+        raise AssertionError(f"timed out after {timeout}s\n" + out[-3000:] + err[-3000:])
+    return subprocess.CompletedProcess(cmd, p.returncode, out, err)
+
+
 @pytest.mark.parametrize("p2p", ["1", "0"])
 @pytest.mark.parametrize("world,ns", [(2, "20,12,10"), (2, "7,9,5"), (2, "3,6,5"), (4, "23,8,6"), (8, "40,6,6"), (8, "9,6,5")])
 def test_slab_solve_multi_gpu(fv, world, ns, p2p):
@@ -27,7 +41,7 @@ def test_slab_solve_multi_gpu(fv, world, ns, p2p):
     port = 29600 + (os.getpid() + world) % 300
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    r = _run_group(cmd, env, timeout=240)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "ok=True" in r.stdout
 
@@ -123,5 +137,5 @@ def test_c_abi_multi_demo(fv, tmp_path, ndev):
     subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "examples", "c_abi_multi_demo.c"), "-o", exe, fv.LIB_PATH, f"-Wl,-rpath,{libdir}", "-lm"],
                    check=True)
-    r = subprocess.run([exe, str(ndev), "64"], capture_output=True, text=True, timeout=600)
+    r = _run_group([exe, str(ndev), "64"], dict(os.environ), timeout=240)
     assert r.returncode == 0 and "c_abi_multi_demo ok" in r.stdout, r.stdout + r.stderr

@@ -381,6 +381,69 @@ def test_theis_transient(fv, orc):
     assert np.max(np.abs(us[-1] - uso[-1])) <= 1e-6
 
 
+@pytest.mark.parametrize("grid", ["box", "circle"])
+def test_device_controller_matches_host_controller(fv, grid, monkeypatch):
+    """fvb_integrate (controller inside the library; one cooperative launch per step-doubling attempt on small
+    systems) against the Python restatement of src/transient.jl:78-154 driving one fvb_step per solve: identical
+    accepted times, attempts and solve counts, states equal to solver tolerance -- forward (adaptive and fixed
+    steppers), with a time-dependent right-hand side, and for the adjoint operator; the same with the
+    cooperative kernel switched off (FVB_COOP_OFF).  "box": diagonal format; "circle": CSR (Dirichlet ring)."""
+    fvt = __import__("importlib").import_module("fvb200.transient")
+    ns = [21, 21, 2]
+    _, nb, aol, vol = fv.regulargrid([-10, -10, 0], [10, 10, 1], ns, want_coords=False)
+    N = int(np.prod(ns))
+    rng = np.random.default_rng(5)
+    k = np.exp(np.log(1e-3) + 0.5 * rng.standard_normal(nb.shape[0]))
+    plane = ns[1] * ns[2]
+    if grid == "box":
+        dn = np.concatenate([np.arange(1, plane + 1), np.arange(N - plane + 1, N + 1)])
+    else:
+        co, *_ = fv.regulargrid([-10, -10, 0], [10, 10, 1], ns)
+        dn = np.flatnonzero(co[0] ** 2 + co[1] ** 2 >= 81.0) + 1
+    dh = np.zeros(dn.size)
+    src = np.zeros(N)
+    free = np.setdiff1d(np.arange(1, N + 1), dn)
+    src[free[free.size // 2] - 1] = -1e-2
+    Ss, u0, tspan = 0.05, np.zeros(N), (0.0, 400.0)
+    args = (u0, tspan, Ss, vol, nb, aol, k, src, dn, dh)
+
+    def run(**kw):
+        st = {}
+        us, ts = fv.backwardeulerintegrate(*args, atol=1e-5, dt0=0.5, rtol=1e-11, stats=st, **kw)
+        return np.array(us), np.array(ts), st
+
+    calls_d, calls_h = [], []
+    ud, td, sd = run(callback=lambda t, dt: calls_d.append((t, dt)))
+    uh, th, sh = run(controller="host", callback=lambda t, dt: calls_h.append((t, dt)))
+    assert fv.System().assemble(nb, aol, k, src, dn, dh).spmv_format()[0] == ("dia" if grid == "box" else "csr")
+    assert np.array_equal(td, th) and sd["steps"] == sh["steps"] and sd["linear_solves"] == sh["linear_solves"]
+    assert calls_d == calls_h and sd["attempts"] >= sd["steps"]
+    assert np.max(np.abs(ud - uh)) <= 1e-9 * max(1.0, np.max(np.abs(uh)))
+    monkeypatch.setenv("FVB_COOP_OFF", "1")
+    un, tn, sn = run()
+    monkeypatch.delenv("FVB_COOP_OFF")
+    assert np.array_equal(tn, td) and sn["linear_solves"] == sd["linear_solves"] and np.max(np.abs(un - ud)) <= 1e-9 * max(1.0, np.max(np.abs(ud)))
+    # fixed stepper
+    uf, tf, sf = run(stepper=fvt.fixedbackwardeulerstep)
+    ug, tg, sg = run(stepper=fvt.fixedbackwardeulerstep, controller="host")
+    assert np.array_equal(tf, tg) and sf["linear_solves"] == sg["linear_solves"] == sf["steps"] and np.max(np.abs(uf - ug)) <= 1e-9
+    # time-dependent right-hand side (general path: one fvb_step per solve)
+    s = fv.System().assemble(nb, aol, k, src, dn, dh)
+    b0 = s.b()
+    getb = lambda t: b0 * (1.0 + 0.5 * math.sin(t / 50.0))  # noqa: E731
+    u1, t1, s1 = run(getb=getb)
+    u2, t2, s2 = run(getb=getb, controller="host")
+    assert np.array_equal(t1, t2) and s1["linear_solves"] == s2["linear_solves"] and np.max(np.abs(u1 - u2)) <= 1e-9
+    # adjoint operator with a forcing
+    nf = b0.size
+    g0 = rng.standard_normal(nf) * 1e-3
+    dgdu = lambda t: g0 * math.exp(-t / 200.0)  # noqa: E731
+    a_args = (dgdu, tspan, Ss, vol, nb, aol, k, src, dn, dh)
+    l1, tl1 = fv.adjointintegrate(*a_args, atol=1e-6, dt0=0.5, rtol=1e-11)
+    l2, tl2 = fv.adjointintegrate(*a_args, atol=1e-6, dt0=0.5, rtol=1e-11, controller="host")
+    assert tl1 == tl2 and np.max(np.abs(np.array(l1) - np.array(l2))) <= 1e-9 * max(1.0, np.max(np.abs(np.array(l2))))
+
+
 def test_scaled_recurrence_matches_unscaled(fv, orc):
     """Cold-started steady Jacobi solves on the diagonal format run CG on D^-1/2 A D^-1/2 (unit diagonal, no
     D^-1 reads).  Same iterates as Jacobi-PCG on A up to rounding: heads, iteration count and the recorded
@@ -447,11 +510,12 @@ def test_scaled_recurrence_matches_unscaled(fv, orc):
 
 
 @pytest.mark.parametrize("ns", [[40, 64, 64], [100, 100, 2], [60, 150, 2], [50, 33, 7], [60, 5, 9], [18, 11, 7],
-                                [700, 2, 2]])
+                                [700, 2, 2], [7, 1024, 512]])
 def test_dia_tma_kernel_bitwise(fv, ns):
     """The TMA-staged diagonal kernel (dia_tma.cuh) against the per-thread-load kernel and the CSR kernel:
     bit-identical products (interior tiles from shared memory, edge tiles from global memory; near and far,
-    even and odd offsets), the same solves, the transient operator."""
+    even and odd offsets; [7, 1024, 512]: planes of 2^19 rows, i.e. the plane-blocked tile order), the same solves,
+    the transient operator."""
     nb, aol, lnkf, src, dn, dh, vol = box_problem(fv, ns, 1.2)
     src = 1e-6 * np.random.default_rng(4).standard_normal(src.size)
     src[dn - 1] = 0
