@@ -444,7 +444,7 @@ class System:
     def preconditioner(self):
         a, l = C.c_int(), C.c_int()
         check(lib().fvb_get_preconditioner(self._h, C.byref(a), C.byref(l)))
-        return ("mg" if a.value == 1 else "jacobi"), l.value
+        return {0: "jacobi", 1: "mg", 2: "amg"}[a.value], l.value
 
     def set_spmv_format(self, fmt):
         """0 = automatic (diagonal copy when the pattern allows), 1 = always CSR, 2 = diagonal copy with the
@@ -710,7 +710,7 @@ def solvediffusion(neighbors, areasoverlengths, conductivities, sources, dirichl
         s.set_preconditioner("mg")  # before assemble: silently stays on Jacobi when the matrix does not qualify
     s.assemble(neighbors, areasoverlengths, conductivities, sources, dirichletnodes, dirichletheads,
                metaindex, logtransformconductivity)
-    if precond == "mg" and s.preconditioner()[0] != "mg":
-        raise _lib.FVBError(1, "multigrid needs a box-structured 7-point matrix; use precond='auto' or 'jacobi'")
+    if precond == "mg" and s.preconditioner()[0] not in ("mg", "amg"):
+        raise _lib.FVBError(1, "no multigrid hierarchy could be built for this matrix; use precond='auto' or 'jacobi'")
     head, _, ch = s.solve(rtol=rtol, maxiter=maxiter)
     return head, ch, SparseMatrixCSC(s), s.b(), s.freenode()

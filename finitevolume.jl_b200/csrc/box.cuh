@@ -47,10 +47,13 @@ k_box_check(BoxDesc B, const longlong2 *__restrict__ nb, const int *__restrict__
   const bool halo_plane = G.e_lo < G.p_lo;
   const long long base_owned = faces_before(G, G.p_lo, 1, 1);
   bool bad_list = false, bad_shift = false;
+  // (node counts of a rank fit 32 bits: 32-bit divisions, several times cheaper than 64-bit ones)
+  const unsigned plane32 = (unsigned)plane, n332 = (unsigned)G.n3;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nodes; t += (long long)gridDim.x * blockDim.x) {
-    const long long i1 = G.e_lo + t / plane;
-    const long long rem = t % plane;
-    const long long i2 = rem / G.n3 + 1, i3 = rem % G.n3 + 1;
+    const unsigned q1 = (unsigned)t / plane32, rem32 = (unsigned)t - q1 * plane32, q2 = rem32 / n332;
+    const long long i1 = G.e_lo + q1;
+    const long long rem = rem32;
+    const long long i2 = q2 + 1, i3 = rem32 - q2 * n332 + 1;
     const long long lin = i3 + G.n3 * (i2 - 1) + plane * (i1 - 1);
     if (i1 < G.p_lo) {
       const longlong2 p = nb[rem];
@@ -181,8 +184,9 @@ k_box_values(BoxDesc B, FaceC fc, const int *__restrict__ nodemap, const double 
     const int m = nodemap[tl];
     if (m < 0) continue;
     const long long r = m;
-    const long long i1 = G.p_lo + tl / plane, rem = tl % plane;
-    const long long i2 = rem / G.n3 + 1, i3 = rem % G.n3 + 1;
+    const unsigned q1 = (unsigned)tl / (unsigned)plane, rem32 = (unsigned)tl - q1 * (unsigned)plane, q2 = rem32 / (unsigned)G.n3;
+    const long long i1 = G.p_lo + q1, rem = rem32;
+    const long long i2 = q2 + 1, i3 = rem32 - q2 * (unsigned)G.n3 + 1;
     double dv = 0.0, bv = sources ? sources[tl] : 0.0;
     bool first = true;
     unsigned mk = 0;

@@ -47,6 +47,7 @@ struct BoxDesc;   // box.cuh
 struct Comm;      // nccl_dyn.h
 struct PeerState; // fvb200.cu (peer.cuh tables)
 struct MgState;   // fvb200.cu (mg.cuh hierarchy)
+struct AmgState;  // fvb200.cu (amg.cuh hierarchy)
 
 }  // namespace fvb
 
@@ -150,6 +151,7 @@ struct fvb_handle_s {
   int mg_nu = 2;
   double mg_omega = 0.8, mg_oc = 1.5;
   fvb::MgState *mg = nullptr;
+  fvb::AmgState *amg = nullptr;   // aggregation AMG on CSR rows for matrices mg.cuh does not cover (amg.cuh)
 
   // in-situ SpMV launch timing (fvb_set_profiling)
   int prof_stride = 0;

@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cstdlib>
 
+#include "amg.cuh"
 #include "arena.h"
 #include "assemble.cuh"
 #include "box.cuh"
@@ -44,6 +45,12 @@ struct PeerState {
   HaloPlanDev push = {}, wait = {};
   unsigned long long red_seq = 0, halo_seq = 0;
   std::vector<uint8_t> last_blobs;      // what the open mappings correspond to
+};
+struct AmgState {
+  bool ready = false;
+  int nlev = 0;
+  AmgLevel lev[kAmgMaxLevels];
+  std::vector<void *> owned;  // every device array of the hierarchy (freed together)
 };
 struct MgState {
   bool ready = false;
@@ -115,6 +122,7 @@ cudaError_t memcpy_sync(cudaStream_t st, void *dst, const void *src, size_t byte
 }
 
 int ensure_csr(fvb_handle h);  // box problems: CSR image on first demand (defined with the box code below)
+void amg_free(fvb_handle h);   // aggregation-AMG hierarchy (defined with the multigrid code below)
 
 int grid_for(int64_t n) { return std::max(1, cdiv(n, kBlock)); }
 int vgrid(fvb_handle h, int64_t n) { return std::max(1, std::min(cdiv(n, kBlock), h->num_sms * 8)); }
@@ -145,6 +153,7 @@ void free_problem(fvb_handle h) {
     h->mg->ready = false;
     h->mg->nlev = 0;
   }
+  amg_free(h);
   h->hist_cap = 0;
   h->assembled = false;
   h->halo_ready = false;
@@ -941,6 +950,207 @@ int mg_vcycle(fvb_handle h, const double *r) {
   return FVB_OK;
 }
 
+// ---- aggregation AMG on CSR rows (amg.cuh) ---------------------------------------------------------------------------
+void amg_free(fvb_handle h) {
+  if (!h->amg) return;
+  for (void *p : h->amg->owned) {
+    unsigned char *q = static_cast<unsigned char *>(p);
+    dfree(h, q);
+  }
+  h->amg->owned.clear();
+  h->amg->ready = false;
+  h->amg->nlev = 0;
+}
+
+template <typename T>
+int amg_alloc(fvb_handle h, T **p, int64_t n) {
+  FVB_TRY(dalloc(h, p, n));
+  h->amg->owned.push_back(*p);
+  return FVB_OK;
+}
+
+// One pairwise-aggregation pass on a CSR matrix: agg[n] (row -> aggregate) and the number of aggregates.
+int amg_pairwise(fvb_handle h, int n, const int *rowptr, const int *colidx, const double *vals, int *agg, int *nc_out,
+                 int *d_match, int *d_prop, int *d_flag, int *d_scratch) {
+  cudaStream_t st = h->stream;
+  const int g = grid_for(n);
+  FVB_CUDA(cudaMemsetAsync(d_match, 0xFF, sizeof(int) * (size_t)n, st));
+  for (int round = 0; round < 4; ++round) {
+    k_amg_propose<<<g, kBlock, 0, st>>>(n, rowptr, colidx, vals, d_match, d_prop);
+    k_amg_accept<<<g, kBlock, 0, st>>>(n, d_prop, d_match);
+  }
+  k_amg_roots<<<g, kBlock, 0, st>>>(n, d_match, d_flag);
+  exclusive_scan(d_flag, n, d_flag, d_scratch, st, &h->tm.kernel_launches);
+  k_amg_number<<<g, kBlock, 0, st>>>(n, d_match, d_flag, agg);
+  h->tm.kernel_launches += 10;
+  FVB_CUDA(memcpy_sync(st, nc_out, d_flag + n, sizeof(int), cudaMemcpyDeviceToHost));
+  return FVB_OK;
+}
+
+// Galerkin coarse matrix of `fine` for the aggregation agg (nc aggregates); the arrays are owned by the hierarchy
+// when keep is set, else by the caller (tmp_*: freed by the caller).  *ok = false: a coarse row overflowed.
+int amg_galerkin(fvb_handle h, int n, const int *rowptr, const int *colidx, const double *vals, const int *agg, int nc,
+                 int **memptr_out, int **mem_out, int **crowptr_out, int **ccol_out, double **cval_out, int *cnnz_out,
+                 bool keep, int *d_scratch, bool *ok) {
+  cudaStream_t st = h->stream;
+  *ok = false;
+  int *memptr = nullptr, *mem = nullptr, *cursor = nullptr, *crowptr = nullptr, *ccol = nullptr, *d_over = nullptr;
+  double *cval = nullptr;
+  auto A = [&](auto **p, int64_t cnt) { return keep ? amg_alloc(h, p, cnt) : dalloc(h, p, cnt); };
+  FVB_TRY(A(&memptr, (int64_t)nc + 2));
+  FVB_TRY(A(&mem, n));
+  FVB_TRY(dalloc(h, &cursor, (int64_t)nc + 2));
+  FVB_TRY(dalloc(h, &d_over, 1));
+  FVB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * ((size_t)nc + 2), st));
+  FVB_CUDA(cudaMemsetAsync(d_over, 0, sizeof(int), st));
+  k_amg_count_members<<<grid_for(n), kBlock, 0, st>>>(n, agg, cursor);
+  exclusive_scan(cursor, nc, memptr, d_scratch, st, &h->tm.kernel_launches);
+  FVB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * ((size_t)nc + 2), st));
+  k_amg_fill_members<<<grid_for(n), kBlock, 0, st>>>(n, agg, memptr, cursor, mem);
+  k_amg_sort_members<<<grid_for(nc), kBlock, 0, st>>>(nc, memptr, mem);
+  FVB_TRY(A(&crowptr, (int64_t)nc + 2));
+  const int gg = std::max(1, cdiv(nc, 128));
+  k_amg_galerkin<false><<<gg, 128, 0, st>>>(nc, memptr, mem, rowptr, colidx, vals, agg, n, nullptr, nullptr, nullptr, cursor, d_over);
+  exclusive_scan(cursor, nc, crowptr, d_scratch, st, &h->tm.kernel_launches);
+  int cnnz = 0, over = 0;
+  FVB_CUDA(cudaMemcpyAsync(&cnnz, crowptr + nc, sizeof(int), cudaMemcpyDeviceToHost, st));
+  FVB_CUDA(memcpy_sync(st, &over, d_over, sizeof(int), cudaMemcpyDeviceToHost));
+  h->tm.kernel_launches += 4;
+  if (!over) {
+    FVB_TRY(A(&ccol, std::max(cnnz, 1)));
+    FVB_TRY(A(&cval, std::max(cnnz, 1)));
+    k_amg_galerkin<true><<<gg, 128, 0, st>>>(nc, memptr, mem, rowptr, colidx, vals, agg, n, crowptr, ccol, cval, nullptr, d_over);
+    h->tm.kernel_launches++;
+    *ok = true;
+  }
+  dfree(h, cursor); dfree(h, d_over);
+  *memptr_out = memptr; *mem_out = mem; *crowptr_out = crowptr; *ccol_out = ccol; *cval_out = cval; *cnnz_out = cnnz;
+  return FVB_OK;
+}
+
+// Build the hierarchy from the CSR rows of this rank (off-rank couplings are left out: block-local).
+int amg_setup(fvb_handle h) {
+  if (!h->amg) h->amg = new AmgState();
+  amg_free(h);
+  AmgState &M = *h->amg;
+  if (!h->rowptr || h->nf_local < 2 || h->nnz >= INT_MAX - 1) return FVB_OK;
+  cudaStream_t st = h->stream;
+  AmgLevel *L = &M.lev[0];
+  *L = AmgLevel{};
+  L->n = (int)h->nf_local; L->nnz = (int)h->nnz;
+  L->rowptr = h->rowptr; L->colidx = h->colidx; L->vals = h->vals;
+  int nlev = 1;
+  int *d_match = nullptr, *d_prop = nullptr, *d_flag = nullptr, *d_scratch = nullptr, *d_a1 = nullptr, *d_a2 = nullptr;
+  const int64_t n0 = L->n;
+  FVB_TRY(dalloc(h, &d_match, n0 + 2)); FVB_TRY(dalloc(h, &d_prop, n0 + 2)); FVB_TRY(dalloc(h, &d_flag, n0 + 2));
+  FVB_TRY(dalloc(h, &d_scratch, scan_scratch_ints(n0 + 2))); FVB_TRY(dalloc(h, &d_a1, n0 + 2)); FVB_TRY(dalloc(h, &d_a2, n0 + 2));
+  int status = FVB_OK;
+  auto fin = [&](int s) {
+    dfree(h, d_match); dfree(h, d_prop); dfree(h, d_flag); dfree(h, d_scratch); dfree(h, d_a1); dfree(h, d_a2);
+    return s;
+  };
+#define AMG_TRY(expr) do { status = (expr); if (status != FVB_OK) { amg_free(h); return fin(status); } } while (0)
+  while (true) {
+    L = &M.lev[nlev - 1];
+    const int n = L->n;
+    AMG_TRY(amg_alloc(h, &L->dinv, n));
+    AMG_TRY(amg_alloc(h, &L->x, n));
+    AMG_TRY(amg_alloc(h, &L->t, n));
+    if (nlev > 1) AMG_TRY(amg_alloc(h, &L->r, n));
+    k_amg_dinv<<<grid_for(n), kBlock, 0, st>>>(n, L->rowptr, L->colidx, L->vals, L->dinv);
+    h->tm.kernel_launches++;
+    if (n <= kAmgCoarsest || nlev >= kAmgMaxLevels) break;
+    // double pairwise aggregation: pair the rows, pair the pairs on the intermediate Galerkin matrix
+    int n1 = 0, n2 = 0;
+    AMG_TRY(amg_pairwise(h, n, L->rowptr, L->colidx, L->vals, d_a1, &n1, d_match, d_prop, d_flag, d_scratch));
+    int *m1p = nullptr, *m1 = nullptr, *r1 = nullptr, *c1 = nullptr;
+    double *v1 = nullptr;
+    int nnz1 = 0;
+    bool ok = false;
+    AMG_TRY(amg_galerkin(h, n, L->rowptr, L->colidx, L->vals, d_a1, n1, &m1p, &m1, &r1, &c1, &v1, &nnz1, false, d_scratch, &ok));
+    bool stop = !ok;
+    if (ok) {
+      status = amg_pairwise(h, n1, r1, c1, v1, d_a2, &n2, d_match, d_prop, d_flag, d_scratch);
+      if (status == FVB_OK) stop = n2 > (int)(0.8 * n) || n2 < 1;
+    }
+    dfree(h, m1p); dfree(h, m1); dfree(h, r1); dfree(h, c1); dfree(h, v1);
+    if (status != FVB_OK) { amg_free(h); return fin(status); }
+    if (stop) break;
+    AMG_TRY(amg_alloc(h, &L->agg, n));
+    k_amg_compose<<<grid_for(n), kBlock, 0, st>>>(n, d_a1, d_a2, L->agg);
+    h->tm.kernel_launches++;
+    int *crow = nullptr, *ccol = nullptr;
+    double *cval = nullptr;
+    int cnnz = 0;
+    AMG_TRY(amg_galerkin(h, n, L->rowptr, L->colidx, L->vals, L->agg, n2, &L->memptr, &L->mem, &crow, &ccol, &cval, &cnnz, true, d_scratch, &ok));
+    if (!ok) { L->agg = nullptr; break; }  // a coarse row too long for the merge buffers: this level is the coarsest
+    L->nc = n2;
+    AmgLevel &C = M.lev[nlev];
+    C = AmgLevel{};
+    C.n = n2; C.nnz = cnnz; C.rowptr = crow; C.colidx = ccol; C.vals = cval;
+    ++nlev;
+  }
+#undef AMG_TRY
+  M.nlev = nlev;
+  M.ready = true;
+  FVB_CUDA(cudaStreamSynchronize(st));
+  return fin(FVB_OK);
+}
+
+// z = M^-1 r : one V(nu,nu) cycle from a zero initial guess; the result lands in lev[0].x.
+int amg_vcycle(fvb_handle h, const double *r) {
+  AmgState &M = *h->amg;
+  cudaStream_t st = h->stream;
+  const int nu = h->mg_nu;
+  const double om = h->mg_omega, oc = h->mg_oc;
+  M.lev[0].r = const_cast<double *>(r);
+  for (int l = 0; l + 1 < M.nlev; ++l) {
+    AmgLevel &L = M.lev[l];
+    const int g = grid_for(L.n);
+    double *cur = L.t, *oth = L.x;  // 2*nu-1 swaps in total: start in t to finish in x
+    k_amg_smooth0<<<g, kBlock, 0, st>>>(L, L.r, cur, om, h->scal);
+    for (int s = 1; s < nu; ++s) {
+      k_amg_smooth<<<g, kBlock, 0, st>>>(L, L.r, cur, oth, om, h->scal);
+      std::swap(cur, oth);
+    }
+    k_amg_restrict<<<grid_for(L.nc), kBlock, 0, st>>>(L, L.r, cur, M.lev[l + 1].r, h->scal);
+    h->tm.kernel_launches += nu + 1;
+  }
+  {
+    AmgLevel &L = M.lev[M.nlev - 1];
+    k_amg_coarse_solve<<<1, kBlock, 0, st>>>(L, L.r, L.x, L.t, om, kAmgCoarseSweeps, h->scal);
+    h->tm.kernel_launches++;
+  }
+  for (int l = M.nlev - 2; l >= 0; --l) {
+    AmgLevel &L = M.lev[l];
+    const int g = grid_for(L.n);
+    double *cur = ((nu - 1) % 2 == 0) ? L.t : L.x;
+    double *oth = cur == L.t ? L.x : L.t;
+    k_amg_prolong<<<g, kBlock, 0, st>>>(L, M.lev[l + 1].x, cur, oc, h->scal);
+    for (int s = 0; s < nu; ++s) {
+      k_amg_smooth<<<g, kBlock, 0, st>>>(L, L.r, cur, oth, om, h->scal);
+      std::swap(cur, oth);
+    }
+    h->tm.kernel_launches += nu + 1;
+  }
+  return FVB_OK;
+}
+
+// Which hierarchy serves precond kind 1: the geometric one of mg.cuh when the matrix is box-structured, else the
+// algebraic one on the CSR rows (single rank).
+bool use_geometric_mg(fvb_handle h) { return h->precond_request == 1 && h->mg && h->mg->ready && h->fmt_request != 1; }
+bool use_amg(fvb_handle h) {
+  return h->precond_request == 1 && !use_geometric_mg(h) && h->nranks == 1 && h->amg && h->amg->ready;
+}
+int precond_setup(fvb_handle h) {
+  FVB_TRY(mg_setup(h, true));
+  if (!(h->mg && h->mg->ready) && h->nranks == 1) {
+    FVB_TRY(ensure_csr(h));
+    if (h->rowptr) FVB_TRY(amg_setup(h));
+  }
+  return FVB_OK;
+}
+
 // CG preconditioned by the V-cycle, steady operator only.  x0 (if any) already in h->x.
 int pcg_mg_run(fvb_handle h, const double *rhs, bool have_x0, double rtol, int64_t maxiter, int64_t *iters,
                int *converged);
@@ -1048,7 +1258,7 @@ int pcg_mg_run(fvb_handle h, const double *rhs, bool have_x0, double rtol, int64
   cudaStream_t st = h->stream;
   const int fin = h->nranks == 1 ? 1 : 0;
   const int vg = vgrid(h, n);
-  MgState &M = *h->mg;
+  const bool use_amg = !(h->mg && h->mg->ready && h->fmt_request != 1);  // else the geometric hierarchy of mg.cuh
   FVB_TRY(ensure_hist(h, maxiter));
   h->last_solve_scaled = false;
   h->prof_seen = 0;
@@ -1071,8 +1281,9 @@ int pcg_mg_run(fvb_handle h, const double *rhs, bool have_x0, double rtol, int64
   while (!stop) {
     int64_t todo = std::min<int64_t>(batch, maxiter - enq);
     for (int64_t it = 0; it < todo; ++it) {
-      FVB_TRY(mg_vcycle(h, h->r));
-      const double *z = M.lev[0].x;
+      if (use_amg) FVB_TRY(amg_vcycle(h, h->r));
+      else FVB_TRY(mg_vcycle(h, h->r));
+      const double *z = use_amg ? h->amg->lev[0].x : h->mg->lev[0].x;
       k_mgpcg_rz<<<vg, kBlock, 0, st>>>(n, h->r, z, h->partials, h->ticket, h->scal, fin);
       h->tm.kernel_launches++;
       if (!fin) FVB_TRY(allreduce_fin(h, 1, FIN_RZ));
@@ -1220,6 +1431,7 @@ int fvb_destroy(fvb_handle h) {
   cudaStreamSynchronize(h->stream);
   free_problem(h);
   delete h->mg;
+  delete h->amg;
   if (h->peer) {
     for (int r = 0; r < kMaxRanks; ++r) {
       if (h->peer->opened_u[r]) cudaIpcCloseMemHandle(h->peer->opened_u[r]);
@@ -1434,7 +1646,7 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
       h->d_dsorted = d_dsorted; h->d_dsorted_slot = d_dsorted_slot; h->nd_sorted = nd_sorted;  // retained
       d_dsorted = nullptr; d_dsorted_slot = nullptr;
       A_TRY(box_install(h, B));
-      if (h->precond_request == 1) A_TRY(mg_setup(h, true));
+      if (h->precond_request == 1) A_TRY(precond_setup(h));
       A_CUDA(cudaEventRecord(h->ev[2], st));
       int herr[ERR_COUNT];
       A_CUDA(cudaMemcpyAsync(herr, d_err, sizeof(herr), cudaMemcpyDeviceToHost, st));
@@ -1560,7 +1772,7 @@ int fvb_assemble(fvb_handle h, int64_t n_nodes, int64_t node_lo1, int64_t node_h
     h->tm.kernel_launches++;
   }
   if (h->fmt_request != 1) A_TRY(build_dia(h, true));
-  if (h->precond_request == 1) A_TRY(mg_setup(h, true));
+  if (h->precond_request == 1) A_TRY(precond_setup(h));
   A_CUDA(cudaEventRecord(h->ev[2], st));
   A_CUDA(cudaStreamSynchronize(st));
   A_CUDA(cudaGetLastError());
@@ -1640,6 +1852,7 @@ int fvb_update_values(fvb_handle h, const double *cond, int64_t n_cond, int logk
     dfree(h, h->rowptr); dfree(h, h->colidx); dfree(h, h->vals);  // a CSR image built on demand is stale now
   } else if (h->dia_on) st_dia = build_dia(h, false);
   if (st_dia == FVB_OK && h->mg && h->mg->ready) st_mg = mg_setup(h, false);
+  if (st_dia == FVB_OK && st_mg == FVB_OK && h->amg && h->amg->ready) st_mg = amg_setup(h);  // aggregates follow the values
   cudaEventRecord(h->ev[2], st);
   int herr[ERR_COUNT];
   cudaError_t e = cudaMemcpyAsync(herr, d_err, sizeof(herr), cudaMemcpyDeviceToHost, st);
@@ -1791,7 +2004,7 @@ int fvb_assemble_regulargrid(fvb_handle h, const double mins[3], const double ma
   }
   h->box_implicit = true;
   G_TRY(box_install(h, B));
-  if (h->precond_request == 1) G_TRY(mg_setup(h, true));
+  if (h->precond_request == 1) G_TRY(precond_setup(h));
   G_CUDA(cudaEventRecord(h->ev[2], st));
   G_CUDA(cudaStreamSynchronize(st));
   G_CUDA(cudaGetLastError());
@@ -2065,7 +2278,7 @@ int fvb_solve(fvb_handle h, double rtol, int64_t maxiter, const double *x0_free,
   if (x0_free) FVB_CUDA(cudaMemcpyAsync(h->x, x0_free, sizeof(double) * (size_t)n, cudaMemcpyDefault, st));
   int64_t it = 0;
   int conv = 0;
-  if (h->precond_request == 1 && h->mg && h->mg->ready && h->fmt_request != 1)
+  if (use_geometric_mg(h) || use_amg(h))
     FVB_TRY(pcg_mg_run(h, h->b, x0_free != nullptr, rtol, maxiter, &it, &conv));
   else
     FVB_TRY(pcg_run(h, h->b, x0_free != nullptr, 0.0, rtol, maxiter, &it, &conv));
@@ -2634,17 +2847,19 @@ int fvb_nodehycos2neighborhycos(fvb_handle h, int64_t n_faces, const int64_t *ne
 int fvb_set_preconditioner(fvb_handle h, int kind, int nu, double omega, double oc) {
   FVB_TRY(check_handle(h, false));
   if (kind != 0 && kind != 1) return set_error(FVB_ERR_BAD_INPUT, "preconditioner kind must be 0 (Jacobi) or 1 (multigrid)");
+  if (kind == 1 && h->assembled && h->box_implicit && h->mg && h->mg->ready) { /* hierarchy already there */ }
   if (nu < 0 || nu > 8 || omega < 0 || omega >= 2 || oc < 0) return set_error(FVB_ERR_BAD_INPUT, "bad multigrid parameters");
   h->precond_request = kind;
   if (nu > 0) h->mg_nu = nu;
   if (omega > 0) h->mg_omega = omega;
   if (oc > 0) h->mg_oc = oc;
   if (kind == 1 && h->assembled) {
-    if (!h->mg || !h->mg->ready) FVB_TRY(mg_setup(h, true));
+    if (!(h->mg && h->mg->ready) && !(h->amg && h->amg->ready)) FVB_TRY(precond_setup(h));
     FVB_CUDA(cudaStreamSynchronize(h->stream));
-    if (!h->mg->ready) {
+    if (!use_geometric_mg(h) && !use_amg(h)) {
       h->precond_request = 0;
-      return set_error(FVB_ERR_BAD_INPUT, "multigrid needs a box-structured 7-point matrix (diagonal format with offsets 1, nz, ny*nz)");
+      return set_error(FVB_ERR_BAD_INPUT, "no multigrid hierarchy for this matrix: the geometric one needs a box-structured 7-point "
+                                          "matrix (diagonal format with offsets 1, nz, ny*nz), the algebraic one a single-rank CSR");
     }
   }
   return FVB_OK;
@@ -2652,9 +2867,9 @@ int fvb_set_preconditioner(fvb_handle h, int kind, int nu, double omega, double 
 
 int fvb_get_preconditioner(fvb_handle h, int *active_kind, int *n_levels) {
   FVB_TRY(check_handle(h, true));
-  const bool mg = h->precond_request == 1 && h->mg && h->mg->ready && h->fmt_request != 1;
-  if (active_kind) *active_kind = mg ? 1 : 0;
-  if (n_levels) *n_levels = mg ? h->mg->nlev : 0;
+  const bool mg = use_geometric_mg(h), amg = use_amg(h);
+  if (active_kind) *active_kind = mg ? 1 : (amg ? 2 : 0);
+  if (n_levels) *n_levels = mg ? h->mg->nlev : (amg ? h->amg->nlev : 0);
   return FVB_OK;
 }
 

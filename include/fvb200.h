@@ -316,13 +316,16 @@ int fvb_nodehycos2neighborhycos(fvb_handle h, int64_t n_faces, const int64_t *ne
 
 /* ---- preconditioner ----------------------------------------------------------------------
  * kind 0: Jacobi (default; north_star).  kind 1: aggregation-multigrid V-cycle (the reference
- * preconditions with Ruge-Stueben AMG, src/FiniteVolume.jl:160); needs a box-structured matrix
- * (diagonal format, 3 offsets).  nu = smoothing sweeps per side (>=1), omega = Jacobi damping,
- * oc = coarse-correction scaling; pass 0 for the defaults (2, 0.8, 1.5).
- * Called after fvb_assemble it fails with FVB_ERR_BAD_INPUT when the matrix does not qualify;
+ * preconditions with Ruge-Stueben AMG, src/FiniteVolume.jl:160):
+ *   - box-structured matrices (diagonal format, 3 offsets): geometric 2x2x2 aggregation on the
+ *     diagonal copy (csrc/mg.cuh), also across slab ranks;            active_kind = 1
+ *   - any other matrix, single rank (fracture networks, irregular Dirichlet sets): algebraic
+ *     double-pairwise aggregation on the CSR rows (csrc/amg.cuh);      active_kind = 2
+ * nu = smoothing sweeps per side (>=1), omega = Jacobi damping, oc = coarse-correction scaling;
+ * pass 0 for the defaults (2, 0.8, 1.5).
+ * Called after fvb_assemble it fails with FVB_ERR_BAD_INPUT when no hierarchy can be built;
  * set before, fvb_assemble falls back to Jacobi silently -- check fvb_get_preconditioner.
- * Multi-GPU: every rank applies the multigrid of its own diagonal block.  The transient step
- * (fvb_step) always uses Jacobi. */
+ * The transient step (fvb_step) always uses Jacobi. */
 int fvb_set_preconditioner(fvb_handle h, int kind, int nu, double omega, double oc);
 int fvb_get_preconditioner(fvb_handle h, int *active_kind, int *n_levels);
 
