@@ -5,9 +5,9 @@
 //
 // Set-up, all on the device and deterministic (no floating-point atomics):
 //   * pairwise aggregation by handshaking: every unmatched row proposes to its strongest unmatched neighbour
-//     (most negative a_ij, ties to the smaller index); mutual proposals become pairs; three rounds; the rest stay
-//     singletons.  Applied twice per level ("double pairwise", aggregates of up to four rows) with the
-//     intermediate Galerkin matrix built and dropped.
+//     (most negative a_ij, ties by a symmetric edge hash); mutual proposals become pairs; six rounds; rows left
+//     over join the pair of their strongest paired neighbour (hubs), else stay singletons.  Applied twice per
+//     level ("double pairwise") with the intermediate Galerkin matrix built and dropped.
 //   * Galerkin coarse operator for piecewise-constant prolongation, A_c[I,J] = sum_{i in I, j in J} a_ij: one
 //     thread per coarse row merges its member rows (members ascending, entries in row order => fixed summation
 //     order), columns sorted ascending; count pass, scan, fill pass.
@@ -22,6 +22,9 @@ constexpr int kAmgMaxLevels = 24;
 constexpr int kAmgCoarsest = 512;     // stop coarsening at or below this many rows
 constexpr int kAmgCoarseSweeps = 40;  // even
 constexpr int kAmgMaxRow = 128;       // entries a coarse row may have (more: the hierarchy stops at that level)
+constexpr int kAmgRounds = 6;         // handshake rounds per pairwise pass
+constexpr double kAmgStall = 0.9;     // a level that keeps more than this fraction of its rows ends the hierarchy
+constexpr int kAmgOneCta = 2048;      // coarsest levels up to this size are swept by a single CTA
 
 struct AmgLevel {
   int n, nnz;
@@ -78,15 +81,42 @@ __global__ void k_amg_accept(int n, const int *__restrict__ prop, int *__restric
   const int j = prop[i];
   if (j >= 0 && prop[j] == i) match[i] = j;
 }
-__global__ void k_amg_roots(int n, const int *__restrict__ match, int *__restrict__ isroot) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) isroot[i] = match[i] < 0 || i < match[i];
-}
-__global__ void k_amg_number(int n, const int *__restrict__ match, const int *__restrict__ cid, int *__restrict__ agg) {
+// Rows the handshakes left alone join the pair of their strongest paired neighbour (same edge order), so that hubs
+// -- a fracture intersection whose many neighbours all prefer it -- do not stall the coarsening: attach[i] = that
+// neighbour, or -1 (the row stays a singleton aggregate).
+__global__ void k_amg_attach(int n, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                             const double *__restrict__ vals, const int *__restrict__ match, int *__restrict__ attach) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  int best = -1;
+  double bw = 0.0;
+  unsigned bh = 0u;
+  if (match[i] < 0) {
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+      const int j = colidx[k];
+      if (j == i || j >= n || match[j] < 0) continue;
+      const double w = -vals[k];
+      if (w <= 0.0) continue;
+      const unsigned hk = amg_edge_hash(i, j);
+      if (best < 0 || w > bw || (w == bw && hk > bh)) { bw = w; bh = hk; best = j; }
+    }
+  }
+  attach[i] = best;
+}
+__device__ __forceinline__ int amg_root(int i, const int *__restrict__ match, const int *__restrict__ attach) {
   const int m = match[i];
-  agg[i] = cid[(m < 0 || i < m) ? i : m];
+  if (m >= 0) return min(i, m);
+  const int a = attach[i];
+  return a >= 0 ? min(a, match[a]) : i;
+}
+__global__ void k_amg_roots(int n, const int *__restrict__ match, const int *__restrict__ attach, int *__restrict__ isroot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) isroot[i] = amg_root(i, match, attach) == i;
+}
+__global__ void k_amg_number(int n, const int *__restrict__ match, const int *__restrict__ attach,
+                             const int *__restrict__ cid, int *__restrict__ agg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) agg[i] = cid[amg_root(i, match, attach)];
 }
 __global__ void k_amg_compose(int n, const int *__restrict__ a1, const int *__restrict__ a2, int *__restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -975,14 +975,15 @@ int amg_pairwise(fvb_handle h, int n, const int *rowptr, const int *colidx, cons
   cudaStream_t st = h->stream;
   const int g = grid_for(n);
   FVB_CUDA(cudaMemsetAsync(d_match, 0xFF, sizeof(int) * (size_t)n, st));
-  for (int round = 0; round < 4; ++round) {
+  for (int round = 0; round < kAmgRounds; ++round) {
     k_amg_propose<<<g, kBlock, 0, st>>>(n, rowptr, colidx, vals, d_match, d_prop);
     k_amg_accept<<<g, kBlock, 0, st>>>(n, d_prop, d_match);
   }
-  k_amg_roots<<<g, kBlock, 0, st>>>(n, d_match, d_flag);
+  k_amg_attach<<<g, kBlock, 0, st>>>(n, rowptr, colidx, vals, d_match, d_prop);  // d_prop is free again: attach[]
+  k_amg_roots<<<g, kBlock, 0, st>>>(n, d_match, d_prop, d_flag);
   exclusive_scan(d_flag, n, d_flag, d_scratch, st, &h->tm.kernel_launches);
-  k_amg_number<<<g, kBlock, 0, st>>>(n, d_match, d_flag, agg);
-  h->tm.kernel_launches += 10;
+  k_amg_number<<<g, kBlock, 0, st>>>(n, d_match, d_prop, d_flag, agg);
+  h->tm.kernel_launches += 2 * kAmgRounds + 3;
   FVB_CUDA(memcpy_sync(st, nc_out, d_flag + n, sizeof(int), cudaMemcpyDeviceToHost));
   return FVB_OK;
 }
@@ -1071,7 +1072,7 @@ int amg_setup(fvb_handle h) {
     bool stop = !ok;
     if (ok) {
       status = amg_pairwise(h, n1, r1, c1, v1, d_a2, &n2, d_match, d_prop, d_flag, d_scratch);
-      if (status == FVB_OK) stop = n2 > (int)(0.8 * n) || n2 < 1;
+      if (status == FVB_OK) stop = n2 > (int)(kAmgStall * n) || n2 < 1;
     }
     dfree(h, m1p); dfree(h, m1); dfree(h, r1); dfree(h, c1); dfree(h, v1);
     if (status != FVB_OK) { amg_free(h); return fin(status); }
@@ -1118,8 +1119,20 @@ int amg_vcycle(fvb_handle h, const double *r) {
   }
   {
     AmgLevel &L = M.lev[M.nlev - 1];
-    k_amg_coarse_solve<<<1, kBlock, 0, st>>>(L, L.r, L.x, L.t, om, kAmgCoarseSweeps, h->scal);
-    h->tm.kernel_launches++;
+    if (L.n <= kAmgOneCta) {
+      k_amg_coarse_solve<<<1, kBlock, 0, st>>>(L, L.r, L.x, L.t, om, kAmgCoarseSweeps, h->scal);
+      h->tm.kernel_launches++;
+    } else {
+      // the aggregation stalled before the level got small: the same fixed number of sweeps, one launch each
+      const int g = grid_for(L.n);
+      double *cur = L.t, *oth = L.x;  // kAmgCoarseSweeps is even: an odd number of swaps ends in x
+      k_amg_smooth0<<<g, kBlock, 0, st>>>(L, L.r, cur, om, h->scal);
+      for (int s = 1; s < kAmgCoarseSweeps; ++s) {
+        k_amg_smooth<<<g, kBlock, 0, st>>>(L, L.r, cur, oth, om, h->scal);
+        std::swap(cur, oth);
+      }
+      h->tm.kernel_launches += kAmgCoarseSweeps;
+    }
   }
   for (int l = M.nlev - 2; l >= 0; --l) {
     AmgLevel &L = M.lev[l];

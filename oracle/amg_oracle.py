@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 import scipy.sparse as sp
 
-MAX_LEVELS, COARSEST, COARSE_SWEEPS, MAX_ROW, ROUNDS = 24, 512, 40, 128, 4
+MAX_LEVELS, COARSEST, COARSE_SWEEPS, MAX_ROW, ROUNDS, STALL = 24, 512, 40, 128, 6, 0.9
 
 
 def edge_hash(a, b):
@@ -43,10 +43,20 @@ def pairwise(A):
         i = np.flatnonzero((match < 0) & (prop >= 0))
         mutual = i[prop[prop[i]] == i]
         match[mutual] = prop[mutual]
-    root = (match < 0) | (np.arange(n) < match)
-    cid = np.cumsum(root) - 1
-    agg = np.where(root, cid, cid[np.where(match >= 0, match, 0)])
-    return agg, int(root.sum())
+    # leftovers join the pair of their strongest paired neighbour (k_amg_attach)
+    ok = (rows != cols) & (w > 0) & (match[rows] < 0) & (match[cols] >= 0)
+    r, c, ww, hh = rows[ok], cols[ok], w[ok], hk[ok]
+    order = np.lexsort((-np.arange(r.size), hh, ww, r))
+    r_s = r[order]
+    last = np.flatnonzero(np.r_[r_s[1:] != r_s[:-1], True]) if r_s.size else np.empty(0, np.int64)
+    attach = np.full(n, -1, np.int64)
+    attach[r_s[last]] = c[order][last]
+    idx = np.arange(n)
+    a_safe = np.where(attach >= 0, attach, 0)
+    rootid = np.where(match >= 0, np.minimum(idx, match), np.where(attach >= 0, np.minimum(a_safe, match[a_safe]), idx))
+    isroot = rootid == idx
+    cid = np.cumsum(isroot) - 1
+    return cid[rootid], int(isroot.sum())
 
 
 def galerkin(A, agg, nc):
@@ -72,7 +82,7 @@ class Hierarchy:
             A1 = galerkin(A, a1, n1)
             a2, n2 = pairwise(A1)
             agg = a2[a1]
-            if n2 > 0.8 * n:
+            if n2 > int(STALL * n) or n2 < 1:
                 break
             Ac = galerkin(A, agg, n2)
             if np.max(np.diff(Ac.indptr)) > MAX_ROW:
