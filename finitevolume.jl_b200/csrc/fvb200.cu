@@ -178,7 +178,7 @@ int ensure_workspace(fvb_handle h) {
     // steady solve needs neither, and at 1024^3 on one GPU each is 8.6 GB
     if (h->nranks == 1) {
       FVB_TRY(dalloc(h, &h->u, n + h->n_halo));
-    } else if (h->u_cap < n + h->n_halo) {
+    } else if (h->u_cap < std::max<int64_t>(n + h->n_halo, 1)) {  // (a rank without rows or halo still exports a vector)
       if (h->u) FVB_CUDA(cudaFree(h->u));
       h->u = nullptr;
       h->u_cap = std::max<int64_t>(n + h->n_halo, 1);
