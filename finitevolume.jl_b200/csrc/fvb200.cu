@@ -775,6 +775,9 @@ int mg_setup(fvb_handle h, bool structure) {
     M.ready = false;
     M.nlev = 0;
     M.dist = false;
+    // (a lambda: a rank whose matrix does not qualify must still reach the agreement below -- returning from
+    //  mg_setup here would leave the other ranks alone in a collective)
+    auto build = [&]() -> int {
     if (!h->dia_on || h->dia_K != 3 || h->dia_off[0] != 1) return FVB_OK;
     const int64_t n = h->nf_local, nz = h->dia_off[1], nynz = h->dia_off[2];
     if (nz < 2 || nynz % nz != 0 || n % nynz != 0 || nynz / nz < 2 || n / nynz < 1) return FVB_OK;
@@ -838,6 +841,9 @@ int mg_setup(fvb_handle h, bool structure) {
       ++l;
     }
     M.nlev = l + 1;
+    return FVB_OK;
+    };
+    FVB_TRY(build());
   }
   if (structure && h->nranks > 1 && h->comm && h->comm->comm) {
     // All ranks must take the same path through the solver (its collectives are matched call by

@@ -11,7 +11,7 @@
 namespace fvb {
 
 constexpr int kMaxRanks = 8;
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long kPeerTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;
 
 struct PeerMail {
   double vals[2][kMaxRanks][4];            // [parity][source rank][value]
