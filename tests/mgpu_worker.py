@@ -40,7 +40,13 @@ def main():
     head, x, ch = s.solve(rtol=1e-12, want_x=True)
     scaled = s.pcg_scaling()  # slab-partitioned boxes keep the diagonal format => scaled recurrence on every rank
     # multigrid: every rank preconditions with the V-cycle of its own diagonal block
-    s.set_preconditioner("mg")
+    try:
+        s.set_preconditioner("mg")
+    except fv.FVBError:
+        # every rank agreed that no hierarchy can be built (a rank without rows, single-plane slabs): the loud
+        # failure is the documented behaviour; expected only for the partitions flagged FV_EXPECT_MG=0
+        if os.environ.get("FV_EXPECT_MG", "1") == "1":
+            raise
     head_mg, _, ch_mg = s.solve(rtol=1e-12)
     mg_kind = s.preconditioner()[0]
     s.set_preconditioner("jacobi")
