@@ -105,6 +105,7 @@ struct fvb_handle_s {
   std::vector<int64_t> send_counts, recv_counts;
   std::vector<int64_t> send_first;  // per plan peer: first row of its send list when that list is a contiguous run
   bool send_contig = false;         // every peer's send list is one ascending run (slab partitions: a plane)
+  bool fused_halo = true;           // FVB_FUSED_HALO_OFF unset (read once at fvb_create: getenv is too slow for the solve loop)
   int32_t *send_rows = nullptr;
   double *sendbuf = nullptr;
   int64_t n_send = 0;

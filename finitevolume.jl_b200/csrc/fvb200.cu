@@ -269,7 +269,7 @@ FusedPush fused_push(fvb_handle h) {
   FusedPush fp = {};
   if (h->nranks == 1 || !h->halo_ready || !(h->peer && h->peer->active) || !h->send_contig) return fp;
   PeerState &P = *h->peer;
-  if (P.push.npeers < 1 || P.push.npeers > 2 || getenv("FVB_FUSED_HALO_OFF")) return fp;
+  if (P.push.npeers < 1 || P.push.npeers > 2 || !h->fused_halo) return fp;
   int k = 0;
   for (size_t p = 0; p < h->peers.size(); ++p) {
     if (h->send_counts[p] <= 0) continue;
@@ -364,7 +364,7 @@ int launch_spmv(fvb_handle h, double *vec, double *out, double sigma, bool dot, 
     tma = use_dia_tma(h, vec, L, scaled);
   }
   FusedWait fw = {};
-  FVB_TRY(halo_exchange(h, vec, pushed, (tma && !getenv("FVB_FUSED_HALO_OFF")) ? &fw : nullptr));
+  FVB_TRY(halo_exchange(h, vec, pushed, (tma && h->fused_halo) ? &fw : nullptr));
   PeerRed pr = {nullptr, 0ull};
   int fin = h->nranks == 1 ? 1 : 0;
   if (dot && fuse) fin = red_mode(h, &pr);
@@ -1216,7 +1216,7 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
   // Enqueue iterations in batches; poll the device scalars one batch behind so the GPU
   // never waits for the host.
   int64_t enq = 0;
-  int batch = 8, slot = 0;
+  int batch = n < (1 << 20) ? 4 : 8, slot = 0;  // small systems are launch-bound: fewer iterations enqueued past convergence
   bool have_prev = false;
   bool stop = false;
   while (!stop) {
@@ -1419,6 +1419,7 @@ int fvb_create(int device, fvb_handle *out) {
   }
   if (const char *env = getenv("FVB_PCG_SCALING")) h->scale_request = atoi(env) == 0 ? 1 : 0;  // A/B measurements
   if (const char *env = getenv("FVB_BOX")) h->box_request = atoi(env) == 0 ? 1 : 0;  // A/B: general path only
+  h->fused_halo = getenv("FVB_FUSED_HALO_OFF") == nullptr;                            // A/B: five-launch halo exchange
   if (const char *env = getenv("FVB_SPMV_FORMAT")) {  // initial fvb_set_spmv_format value
     const int f = atoi(env);
     if (f >= 0 && f <= 3) h->fmt_request = f;

@@ -353,6 +353,21 @@ def test_transient_step_matches_oracle(fv, orc):
     assert math.isclose(s.vec_diffnorm(2, 3), np.linalg.norm(s.vec_download(2) - s.vec_download(3)), rel_tol=1e-12)
     with pytest.raises(fv.FVBError, match="time step must be positive"):
         s.step(0, 1, 0.0, 2)
+    # The reference's `linearsolver(A, rhs, x0)` hook (src/transient.jl:136): it is handed At + I/dt and
+    # rhs~ = D^-1 b + u/dt.  What the Julia closure does (julia/FiniteVolumeB200.jl: linearsolver), step by step:
+    # read 1/dt off the shifted diagonal at the row of least cancellation, solve (A + D/dt) x = D .* rhs~ on the device.
+    Mh = (At + sp.identity(D.size) / dt).tocsr()
+    rhs_t = b / D + u / dt
+    scaled_diag = s.diag() / D
+    imin = int(np.argmin(scaled_diag))
+    sigma = Mh[imin, imin] - scaled_diag[imin]
+    assert math.isclose(sigma, 1 / dt, rel_tol=1e-9)
+    s.vec_upload(0, D * rhs_t)
+    s.vec_upload(1, u)
+    it, conv = s.solve_shifted(0, 1, sigma, 2, rtol=1e-13)
+    assert conv and np.allclose(s.vec_download(2), ref, rtol=1e-9, atol=1e-12)
+    with pytest.raises(fv.FVBError, match="non-negative"):
+        s.solve_shifted(0, 1, -1.0, 2)
 
 
 def test_theis_transient(fv, orc):
