@@ -50,49 +50,20 @@ int multi_run_all(fvb_multi m, Fn fn) {
   return FVB_OK;
 }
 
-// Per-rank halo plan from every rank's row range and ascending halo columns (0-based global free indices).
-struct MultiPlan {
-  std::vector<int32_t> peers;
-  std::vector<int64_t> send_counts, recv_counts, send_dst;
-  std::vector<int32_t> send_rows;
-};
+// Per-rank halo plans from the assembled handles (host_util.h: plan_halo_exchange, the port of
+// distributed.halo_plan_from_ranges + send_destinations).
+using MultiPlan = RankHaloPlan;
 int multi_halo_plans(fvb_multi m, std::vector<MultiPlan> &plans) {
   const int P = m->ndev;
   std::vector<int64_t> start((size_t)P), nf((size_t)P);
-  for (int r = 0; r < P; ++r) { start[(size_t)r] = m->h[(size_t)r]->row_start; nf[(size_t)r] = m->h[(size_t)r]->nf_local; }
-  auto owner = [&](int64_t g) {
-    int o = (int)(std::upper_bound(start.begin(), start.end(), g) - start.begin()) - 1;
-    while (o >= 0 && nf[(size_t)o] == 0) --o;  // ranks without rows share their start with the next one
-    return (o >= 0 && g < start[(size_t)o] + nf[(size_t)o]) ? o : -1;
-  };
-  plans.assign((size_t)P, MultiPlan());
-  // recv side: halo columns arrive grouped by owner in ascending rank order (= ascending column order)
-  std::vector<std::vector<std::vector<int32_t>>> send((size_t)P, std::vector<std::vector<int32_t>>((size_t)P));
-  std::vector<std::vector<int64_t>> recv((size_t)P, std::vector<int64_t>((size_t)P, 0));
+  std::vector<std::vector<int64_t>> halo((size_t)P);
   for (int r = 0; r < P; ++r) {
-    const auto &hc = m->h[(size_t)r]->halo_host;
-    for (size_t k = 0; k < hc.size(); ++k) {
-      if (k && hc[k] <= hc[k - 1]) return set_error(FVB_ERR_STATE, "halo columns are not strictly ascending");
-      const int o = owner(hc[k]);
-      if (o < 0 || o == r) return set_error(FVB_ERR_STATE, "a halo column has no owner among the other devices");
-      recv[(size_t)r][(size_t)o]++;
-      send[(size_t)o][(size_t)r].push_back((int32_t)(hc[k] - start[(size_t)o]));
-    }
+    start[(size_t)r] = m->h[(size_t)r]->row_start;
+    nf[(size_t)r] = m->h[(size_t)r]->nf_local;
+    halo[(size_t)r] = m->h[(size_t)r]->halo_host;
   }
-  for (int r = 0; r < P; ++r) {
-    MultiPlan &pl = plans[(size_t)r];
-    for (int p = 0; p < P; ++p) {
-      if (p == r || (send[(size_t)r][(size_t)p].empty() && recv[(size_t)r][(size_t)p] == 0)) continue;
-      pl.peers.push_back(p);
-      pl.send_counts.push_back((int64_t)send[(size_t)r][(size_t)p].size());
-      pl.recv_counts.push_back(recv[(size_t)r][(size_t)p]);
-      pl.send_rows.insert(pl.send_rows.end(), send[(size_t)r][(size_t)p].begin(), send[(size_t)r][(size_t)p].end());
-      // where my first value goes in the peer's vector: its rows, then its halo entries owned by lower ranks
-      const auto &ph = m->h[(size_t)p]->halo_host;
-      const int64_t before = std::lower_bound(ph.begin(), ph.end(), start[(size_t)r]) - ph.begin();
-      pl.send_dst.push_back(nf[(size_t)p] + before);
-    }
-  }
+  const char *why = plan_halo_exchange(start, nf, halo, plans);
+  if (why[0]) return set_error(FVB_ERR_STATE, why);
   return FVB_OK;
 }
 
@@ -137,26 +108,11 @@ int multi_connect(fvb_multi m) {
   });
 }
 
-// closed-form index of the first face node (i1,i2,i3) emits in regulargrid's list (grid.cuh: faces_before)
 inline int64_t multi_faces_before(int64_t n1, int64_t n2, int64_t n3, int64_t i1, int64_t i2, int64_t i3) {
-  const int64_t hx = i1 < n1, hy = i2 < n2;
-  const int64_t pfull = n2 * n3 + (n2 - 1) * n3 + n2 * (n3 - 1);
-  return (i1 - 1) * pfull + (i2 - 1) * (hx * n3 + n3 + (n3 - 1)) + (i3 - 1) * (hx + hy + 1);
+  return regulargrid_faces_before(n1, n2, n3, i1, i2, i3);
 }
-
-// x-planes 1..n1 -> P contiguous slabs balanced by FREE planes (distributed.slab_planes)
-void multi_slab_planes(int64_t n1, int P, bool dirichlet_ends, std::vector<int64_t> &plo, std::vector<int64_t> &phi) {
-  const int64_t fixed = (dirichlet_ends && n1 >= 2 + P) ? 2 : 0;
-  const int64_t free_planes = n1 - fixed, base = free_planes / P, extra = free_planes % P;
-  plo.assign((size_t)P, 0); phi.assign((size_t)P, 0);
-  int64_t at = 1;
-  for (int r = 0; r < P; ++r) {
-    int64_t c = base + (r < extra ? 1 : 0);
-    if (fixed && r == 0) ++c;
-    if (fixed && r == P - 1) ++c;
-    plo[(size_t)r] = at; phi[(size_t)r] = at + c - 1;
-    at += c;
-  }
+inline void multi_slab_planes(int64_t n1, int P, bool dirichlet_ends, std::vector<int64_t> &plo, std::vector<int64_t> &phi) {
+  slab_planes(n1, P, dirichlet_ends, plo, phi);
 }
 
 struct MultiInputs {

@@ -543,3 +543,80 @@ def test_scaled_diagonal_format_across_slabs(fv, orc, world):
         halo = cols[(cols < lo) | (cols >= hi)]
         got[lo:hi] = _dia_rank_emulation(A, lo, hi, halo, offs, s, x)
     assert np.allclose(got, want, rtol=1e-12, atol=1e-15 * np.abs(want).max())
+
+
+def test_cpp_partition_planning_matches_python(fv, tmp_path):
+    """The single-process multi-GPU front end plans its partition in C++ (csrc/host_util.h: slab_planes,
+    regulargrid_faces_before, plan_halo_exchange); the one-process-per-GPU mode plans it in Python
+    (distributed.slab_planes, grid closed form, halo_plan_from_ranges + send_destinations).  Same answers on slab
+    partitions, random irregular partitions and partitions with ranks that own no row."""
+    import importlib
+    import shutil
+    import subprocess
+    d = importlib.import_module("fvb200.distributed")
+    gxx = shutil.which("g++") or "/usr/bin/g++"
+    exe = str(tmp_path / "plan_cli")
+    subprocess.run([gxx, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "plan_cli.cpp")], check=True)
+
+    def run(*args, stdin=None):
+        return subprocess.run([exe, *map(str, args)], input=stdin, capture_output=True, text=True, check=True).stdout
+
+    for n1, P in [(512, 8), (512, 1), (9, 8), (10, 8), (3, 2), (1024, 4), (7, 3), (8, 8)]:
+        for ends in (True, False):
+            got = [tuple(int(v) for v in ln.split()) for ln in run("planes", n1, P, int(ends)).splitlines()]
+            assert got == d.slab_planes(n1, P, ends), (n1, P, ends)
+    # closed-form face offsets against the list regulargrid builds
+    ns = [4, 3, 5]
+    _, nb, _, _ = fv.regulargrid([0, 0, 0], [n - 1 for n in ns], ns, want_coords=False)
+    first = {}
+    for j, a in enumerate(nb[:, 0]):
+        first.setdefault(int(a), j)
+    for i1 in range(1, ns[0] + 1):
+        for i2 in range(1, ns[1] + 1):
+            for i3 in range(1, ns[2] + 1):
+                lin = i3 + ns[2] * (i2 - 1) + ns[1] * ns[2] * (i1 - 1)
+                if lin in first:
+                    assert int(run("faces_before", *ns, i1, i2, i3)) == first[lin]
+    # halo plans
+    rng = np.random.default_rng(11)
+    cases = []
+    plane = 12
+    for P in (2, 3, 8):  # slabs: one plane of the neighbour on each side
+        nf = [plane * int(rng.integers(1, 4)) for _ in range(P)]
+        start = np.concatenate([[0], np.cumsum(nf)[:-1]]).tolist()
+        halos = []
+        for r in range(P):
+            h = []
+            if r > 0:
+                h += list(range(start[r] - plane, start[r]))
+            if r + 1 < P:
+                h += list(range(start[r] + nf[r], start[r] + nf[r] + plane))
+            halos.append(h)
+        cases.append((start, nf, halos))
+    for _ in range(20):  # irregular: random references, some ranks without rows
+        P = int(rng.integers(2, 7))
+        nf = [int(rng.integers(0, 9)) for _ in range(P)]
+        if sum(nf) == 0:
+            nf[0] = 3
+        start = np.concatenate([[0], np.cumsum(nf)[:-1]]).astype(int).tolist()
+        total = sum(nf)
+        halos = []
+        for r in range(P):
+            other = [g for g in range(total) if not (start[r] <= g < start[r] + nf[r])]
+            k = int(rng.integers(0, len(other) + 1)) if other else 0
+            halos.append(sorted(rng.choice(other, size=k, replace=False).tolist()) if k else [])
+        cases.append((start, nf, halos))
+    for start, nf, halos in cases:
+        P = len(nf)
+        text = f"{P}\n" + "".join(f"{start[r]} {nf[r]} {len(halos[r])} " + " ".join(map(str, halos[r])) + "\n" for r in range(P))
+        lines = run("halo", stdin=text).splitlines()
+        assert not lines[0].startswith("error"), lines[0]
+        ranges = [(start[r] + 1, nf[r]) for r in range(P)]  # the Python planner takes 1-based starts and columns
+        halos1 = [np.asarray(h, np.int64) + 1 for h in halos]
+        for r in range(P):
+            blk = {ln.split()[0]: [int(v) for v in ln.split()[1:]] for ln in lines[5 * r:5 * r + 5]}
+            peers, sc, sr, rc = d.halo_plan_from_ranges(r, ranges, halos1)
+            assert blk["peers"] == list(peers) and blk["send_counts"] == list(sc) and blk["recv_counts"] == list(rc)
+            assert blk["send_rows"] == [int(v) for v in sr]
+            assert blk["send_dst"] == d.send_destinations(r, peers, ranges, halos1)
