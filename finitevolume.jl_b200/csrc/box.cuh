@@ -107,7 +107,12 @@ k_box_check_shift(BoxDesc B, const int *__restrict__ nodemap, int *__restrict__ 
 struct FaceFromArray {
   const double *cface;     // per-face conductance in the order of the (slab's) face list
   __device__ __forceinline__ double operator()(const BoxDesc &B, int dir, long long i1, long long i2, long long i3,
-                                               long long rem, long long /*tl*/) const {
+                                               long long rem, long long tl) const {
+    return cface[index(B, dir, i1, i2, i3, rem, tl)];
+  }
+  // position of that face in the (slab's) face list
+  __device__ __forceinline__ long long index(const BoxDesc &B, int dir, long long i1, long long i2, long long i3,
+                                             long long rem, long long /*tl*/) const {
     const GridDesc &G = B.G;
     const long long plane = G.n2 * G.n3;
     const long long shift = (G.e_lo < G.p_lo ? plane : 0) - faces_before(G, G.p_lo, 1, 1);
@@ -121,7 +126,7 @@ struct FaceFromArray {
       case 4: j = faces_before(G, i1, i2, i3) + hx + shift; break;
       default: j = faces_before(G, i1, i2, i3) + hx + hy + shift; break;
     }
-    return cface[j];
+    return j;
   }
 };
 
