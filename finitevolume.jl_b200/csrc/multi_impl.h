@@ -14,6 +14,12 @@
 // exactly the slab list regulargrid(planes=...) would emit -- the +x faces of the plane below gathered on the
 // host (n2*n3 faces), the rest one contiguous block copied straight from the caller's arrays -- and each
 // device verifies its list on the GPU (box.cuh).  Anything else: equal node counts, faces filtered on the host.
+//
+// Invariant the worker threads rely on: between the first and the last cross-device kernel of a collective call no
+// thread may call into the driver in a way that synchronises devices (cudaMalloc / cudaFree map into every peer's
+// address space once peer access is on, and a device that is spinning on a neighbour's flag never becomes idle).
+// Every allocation of a solve therefore happens in multi_connect (vectors, mailboxes) or comes out of the handle's
+// arena, whose chunks are in place after assembly (the temporaries freed there leave gigabytes of free blocks).
 #pragma once
 #include <thread>
 
