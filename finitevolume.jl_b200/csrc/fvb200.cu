@@ -1223,8 +1223,13 @@ int pcg_run(fvb_handle h, const double *rhs, bool have_x0, double sigma, double 
     int64_t todo = std::min<int64_t>(batch, maxiter - enq);
     for (int64_t it = 0; it < todo; ++it) {
       const FusedPush fp = fused_push(h);  // slab ranks over peer memory: the halo push rides on k_update_u
-      if (sc) k_update_u<true><<<vg, kBlock, 0, st>>>(n, nullptr, h->r, h->u, h->x, h->scal, fp, h->ticket + 1);
-      else k_update_u<false><<<vg, kBlock, 0, st>>>(n, h->dinv, h->r, h->u, h->x, h->scal, fp, h->ticket + 1);
+      if (fp.npeers > 0) {
+        if (sc) k_update_u<true, true><<<vg, kBlock, 0, st>>>(n, nullptr, h->r, h->u, h->x, h->scal, fp, h->ticket + 1);
+        else k_update_u<false, true><<<vg, kBlock, 0, st>>>(n, h->dinv, h->r, h->u, h->x, h->scal, fp, h->ticket + 1);
+      } else {
+        if (sc) k_update_u<true, false><<<vg, kBlock, 0, st>>>(n, nullptr, h->r, h->u, h->x, h->scal, fp, h->ticket + 1);
+        else k_update_u<false, false><<<vg, kBlock, 0, st>>>(n, h->dinv, h->r, h->u, h->x, h->scal, fp, h->ticket + 1);
+      }
       h->tm.kernel_launches++;
       FVB_TRY(launch_spmv(h, h->u, h->c, sigma, true, sc, true, &fin, fp.npeers > 0));
       if (!fin) FVB_TRY(allreduce_fin(h, 1, FIN_UC));

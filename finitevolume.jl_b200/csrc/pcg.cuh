@@ -110,7 +110,7 @@ k_pcg_init(int64_t n, const double *__restrict__ rhs, const double *__restrict__
 // fp.npeers > 0 (slab partitions over NVLink peer memory): the thread that produces u[i] of a boundary row also
 // stores it into the neighbour's halo slot, and the CTA drawing the last ticket raises the neighbours' flags --
 // the halo exchange of the next product rides on this kernel instead of a launch of its own (peer.cuh).
-template <bool SC>
+template <bool SC, bool PUSH>
 __global__ void __launch_bounds__(kBlock)
 k_update_u(int64_t n, const double *__restrict__ dinv, const double *__restrict__ r, double *__restrict__ u,
            double *__restrict__ x, const PcgScal *__restrict__ scal, FusedPush fp, unsigned int *ticket) {
@@ -118,23 +118,15 @@ k_update_u(int64_t n, const double *__restrict__ dinv, const double *__restrict_
     // iterations enqueued past convergence do no work, but EVERY halo sequence number must still be raised on the
     // neighbours: a consumer that is not the fused SpMV (k_halo_wait before the per-thread-load or CSR kernels)
     // waits for it unconditionally
-    if (fp.npeers > 0 && blockIdx.x == 0 && (int)threadIdx.x < fp.npeers) st_release_sys(fp.flag[threadIdx.x], fp.seq);
+    if (PUSH && blockIdx.x == 0 && (int)threadIdx.x < fp.npeers) st_release_sys(fp.flag[threadIdx.x], fp.seq);
     return;
   }
   const bool first = scal->iter == 0;
   const double beta = first ? 0.0 : scal->rho / scal->rho_prev;
   const double ap = scal->alpha_prev;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double un;
-    if (first) {
-      un = SC ? r[i] : dinv[i] * r[i];
-    } else {
-      const double ui = u[i];
-      x[i] += ap * ui;
-      un = (SC ? r[i] : dinv[i] * r[i]) + beta * ui;
-    }
-    u[i] = un;
-    if (fp.npeers > 0) {
+  // (PUSH = false is the single-GPU instantiation: exactly the two plain streaming loops)
+  auto push = [&](int64_t i, double un) {
+    if (PUSH) {
       const long long k0 = i - fp.begin[0];
       if (k0 >= 0 && k0 < fp.count[0]) fp.dst[0][k0] = un;
       if (fp.npeers > 1) {
@@ -142,8 +134,23 @@ k_update_u(int64_t n, const double *__restrict__ dinv, const double *__restrict_
         if (k1 >= 0 && k1 < fp.count[1]) fp.dst[1][k1] = un;
       }
     }
+  };
+  if (first) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const double un = SC ? r[i] : dinv[i] * r[i];
+      u[i] = un;
+      push(i, un);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const double ui = u[i];
+      x[i] += ap * ui;
+      const double un = (SC ? r[i] : dinv[i] * r[i]) + beta * ui;
+      u[i] = un;
+      push(i, un);
+    }
   }
-  if (fp.npeers > 0) {
+  if (PUSH) {
     __threadfence_system();  // my remote stores are visible system-wide before the ticket
     __shared__ bool last;
     __syncthreads();
