@@ -119,7 +119,7 @@ def problem_inputs(fv, n, sigma, planes=None, pin=None):
                 lnk_node_lo=k_lo)
 
 
-def implicit_inputs(n, sigma, planes, pin):
+def implicit_inputs(n, sigma, planes, pin, chunk=1 << 24):
     """The same workload described by node values only: ln K of the owned x-planes plus one plane on each side
     (what fvb_assemble_regulargrid takes), the two Dirichlet planes, zero sources (passed as NULL)."""
     N, plane = n ** 3, n * n
@@ -128,7 +128,7 @@ def implicit_inputs(n, sigma, planes, pin):
     lnk_slab = pin((k_hi - k_lo + 1,), np.float64)
     rng = np.random.default_rng(0)
     # the global field is drawn in node order from one stream (same numbers as problem_inputs); stream through it
-    chunk, pos = 1 << 24, 0
+    pos = 0
     while pos < k_hi:
         m = min(chunk, N - pos)
         z = rng.standard_normal(m)

@@ -620,3 +620,24 @@ def test_cpp_partition_planning_matches_python(fv, tmp_path):
             assert blk["peers"] == list(peers) and blk["send_counts"] == list(sc) and blk["recv_counts"] == list(rc)
             assert blk["send_rows"] == [int(v) for v in sr]
             assert blk["send_dst"] == d.send_destinations(r, peers, ranges, halos1)
+
+
+def test_bench_implicit_inputs_describe_the_same_workload(fv):
+    """bench.py --implicit (the 1024^3 runs) draws the node field in chunks and never builds a face list; it must be the
+    very field problem_inputs() draws in one go, slab by slab, so that both input forms time the same workload."""
+    import bench
+    n = 12
+    whole = bench.problem_inputs(fv, n, 1.0)
+    plane = n * n
+    for planes in [(1, n), (1, 4), (5, 9), (10, 12)]:
+        exp = bench.problem_inputs(fv, n, 1.0, planes=planes)
+        imp = bench.implicit_inputs(n, 1.0, planes, lambda shape, dt: np.empty(shape, dt))
+        assert imp["node_range"] == exp["node_range"] and imp["lnk_node_lo"] == exp["lnk_node_lo"]
+        assert np.array_equal(imp["lnk_slab"], exp["lnk_slab"])
+        assert np.array_equal(imp["dn"], exp["dn"]) and np.array_equal(imp["dh"], exp["dh"])
+        lo = exp["lnk_node_lo"]
+        assert np.array_equal(exp["lnk_slab"], whole["lnk_slab"][lo - 1:lo - 1 + exp["lnk_slab"].size])
+    # chunked drawing: force several chunks
+    big = bench.implicit_inputs(40, 1.0, (3, 20), lambda shape, dt: np.empty(shape, dt), chunk=1000)
+    ref = math.log(1e-5) + np.random.default_rng(0).standard_normal(40 ** 3)
+    assert np.array_equal(big["lnk_slab"], ref[big["lnk_node_lo"] - 1:big["lnk_node_lo"] - 1 + big["lnk_slab"].size])
